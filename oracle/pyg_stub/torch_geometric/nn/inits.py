@@ -1,0 +1,21 @@
+"""torch_geometric.nn.inits restated: uniform(size, t) = U(-1/sqrt(size), 1/sqrt(size)); reset(nn)."""
+import math
+
+
+def uniform(size, tensor):
+    if tensor is not None:
+        bound = 1.0 / math.sqrt(size)
+        tensor.data.uniform_(-bound, bound)
+
+
+def reset(nn):
+    def _reset(item):
+        if hasattr(item, 'reset_parameters'):
+            item.reset_parameters()
+
+    if nn is not None:
+        if hasattr(nn, 'children') and len(list(nn.children())) > 0:
+            for item in nn.children():
+                reset(item)
+        else:
+            _reset(nn)
