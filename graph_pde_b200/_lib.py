@@ -1,0 +1,88 @@
+"""ctypes binding of libnnconv_b200.so (C ABI declared in include/nnconv_b200.h).
+
+The product path has NO fallback: if the shared library is missing or the device is not sm_100-class,
+importing / calling raises.  `build()` compiles the library in-tree with nvcc (sm_100a only).
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libnnconv_b200.so')
+CSRC = os.path.join(_HERE, 'csrc')
+
+OK = 0
+PREC = {'fp32': 0, 'f16': 1, 'fp16': 1, 'bf16': 2}
+AGGR = {'add': 0, 'mean': 1}
+FLOW = {'source_to_target': 0, 'target_to_source': 1}
+
+# every symbol include/nnconv_b200.h declares (tests/test_cabi_symbols.py checks the .so exports them)
+SYMBOLS = [
+    'nnconv_last_error', 'nnconv_abi_version', 'nnconv_init', 'nnconv_plan_sizes', 'nnconv_plan_create',
+    'nnconv_plan_destroy', 'nnconv_plan_info', 'nnconv_weights_sizes', 'nnconv_weights_create',
+    'nnconv_weights_destroy', 'nnconv_weights_tc_supported', 'nnconv_edge_features_sizes',
+    'nnconv_edge_features', 'nnconv_apply_sizes', 'nnconv_apply', 'nnconv_gemm_16b',
+    'nnconv_profile_begin', 'nnconv_profile_end',
+]
+
+
+class NNConvLibraryError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile libnnconv_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ['make', '-C', CSRC, '-j', str(min(8, os.cpu_count() or 1))]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+    if res.returncode != 0:
+        raise NNConvLibraryError('building libnnconv_b200.so failed (see output above)')
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NNConvLibraryError(
+            '%s not found: run `python -c "import __graft_entry__ as g; g.build()"` (or make -C %s). '
+            'There is no CPU/PyTorch fallback for the NNConv path.' % (LIB_PATH, CSRC))
+    L = ctypes.CDLL(LIB_PATH)
+    c_i64, c_sz, c_vp, c_int = ctypes.c_int64, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_int
+    P = ctypes.POINTER
+    L.nnconv_last_error.restype = ctypes.c_char_p
+    L.nnconv_last_error.argtypes = []
+    L.nnconv_abi_version.restype = c_int
+    L.nnconv_init.restype = c_int
+    L.nnconv_plan_sizes.argtypes = [c_i64, c_i64, P(c_sz), P(c_sz)]
+    L.nnconv_plan_create.argtypes = [c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_sz, c_vp, c_sz, c_vp, P(c_vp)]
+    L.nnconv_plan_destroy.argtypes = [c_vp]
+    L.nnconv_plan_destroy.restype = None
+    L.nnconv_plan_info.argtypes = [c_vp, P(c_i64), c_int]
+    L.nnconv_weights_sizes.argtypes = [c_int, P(c_int), c_int, c_int, c_int, P(c_sz)]
+    L.nnconv_weights_create.argtypes = [c_int, P(c_int), c_int, c_int, c_int, P(c_vp), P(c_vp), c_vp, c_sz, c_vp,
+                                        P(c_vp)]
+    L.nnconv_weights_destroy.argtypes = [c_vp]
+    L.nnconv_weights_destroy.restype = None
+    L.nnconv_weights_tc_supported.argtypes = [c_vp]
+    L.nnconv_edge_features_sizes.argtypes = [c_vp, c_vp, c_sz, P(c_sz), P(c_sz)]
+    L.nnconv_edge_features.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, P(c_i64)]
+    L.nnconv_apply_sizes.argtypes = [c_vp, c_vp, c_sz, P(c_sz)]
+    L.nnconv_apply.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_sz, c_vp, P(c_i64)]
+    L.nnconv_gemm_16b.argtypes = [c_int, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp]
+    L.nnconv_profile_end.argtypes = [P(ctypes.c_double), P(c_i64), c_int]
+    for name in SYMBOLS:
+        getattr(L, name)
+    _lib = L
+    return L
+
+
+def check(status):
+    if status != OK:
+        msg = lib().nnconv_last_error()
+        raise NNConvLibraryError('libnnconv_b200 error %d: %s' % (status, msg.decode() if msg else '?'))

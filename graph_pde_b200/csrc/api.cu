@@ -1,0 +1,466 @@
+// C-ABI of libnnconv_b200 (declared in include/nnconv_b200.h) and the host-side sequencing of the
+// kernels.  No device allocation and no device synchronisation happens here except in
+// nnconv_plan_create (one-time per graph, returns counts to the host).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nnc {
+
+namespace {
+thread_local char g_err[512] = "";
+}
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- optional event-based profiling ------------------------------------------------------------
+namespace {
+struct ProfRec { int kind; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+cudaEvent_t g_prof_open[PK_COUNT];
+}
+bool prof_enabled() { return g_prof_on; }
+void prof_mark(int kind, cudaStream_t st, bool begin) {
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  if (begin) g_prof_open[kind] = e;
+  else g_prof.push_back(ProfRec{kind, g_prof_open[kind], e});
+}
+
+static size_t esize_of(int prec) { return prec == PREC_FP32 ? 4 : 2; }
+
+// ------------------------------------------------------------------------------------------------
+// prepared weights
+// ------------------------------------------------------------------------------------------------
+struct WeightsLayout {
+  size_t off_W1, off_b1, off_Wh[kMaxLayers], off_bh[kMaxLayers], off_W3p, off_B3, bytes;
+};
+
+static int fill_dims(Weights* W, int n_layers, const int* dims, int cin, int cout, int prec) {
+  NNC_REQUIRE(n_layers >= 1 && n_layers <= kMaxLayers, NNCONV_ERR_ARG, "edge MLP must have 1..%d Linear layers", kMaxLayers);
+  NNC_REQUIRE(prec >= PREC_FP32 && prec <= PREC_BF16, NNCONV_ERR_ARG, "unknown precision %d", prec);
+  NNC_REQUIRE(cin >= 1 && cout >= 1, NNCONV_ERR_ARG, "bad channel counts");
+  NNC_REQUIRE(dims[n_layers] == cin * cout, NNCONV_ERR_ARG,
+              "edge MLP output width %d != in_channels*out_channels = %d", dims[n_layers], cin * cout);
+  memset(W, 0, sizeof(*W));
+  W->n_layers = n_layers;
+  for (int l = 0; l <= n_layers; ++l) {
+    NNC_REQUIRE(dims[l] >= 1, NNCONV_ERR_ARG, "bad layer width");
+    W->dims[l] = dims[l];
+    W->kp[l] = l == 0 ? dims[0] : round_up(dims[l], 64);
+  }
+  W->cin = cin;
+  W->cout = cout;
+  W->cin_p = round_up(cin, 64);
+  W->K = dims[n_layers - 1];
+  W->Kp = round_up(W->K, 64);
+  W->prec = prec;
+  W->esize = esize_of(prec);
+  return NNCONV_OK;
+}
+
+static WeightsLayout layout_weights(const Weights* W) {
+  Carver c(nullptr, ~size_t(0));
+  WeightsLayout L{};
+  const int nl = W->n_layers;
+  if (nl >= 2) {
+    L.off_W1 = c.off; c.take<float>(static_cast<size_t>(W->kp[1]) * W->dims[0]);
+    L.off_b1 = c.off; c.take<float>(W->kp[1]);
+  }
+  for (int l = 2; l <= nl - 1; ++l) {
+    L.off_Wh[l] = c.off; c.take<char>(static_cast<size_t>(W->kp[l]) * W->kp[l - 1] * W->esize);
+    L.off_bh[l] = c.off; c.take<float>(W->kp[l]);
+  }
+  L.off_W3p = c.off; c.take<char>(static_cast<size_t>(W->cout) * W->Kp * W->cin_p * W->esize);
+  L.off_B3 = c.off; c.take<float>(static_cast<size_t>(W->cin) * W->cout);
+  L.bytes = c.off;
+  return L;
+}
+
+size_t weights_bytes(int n_layers, const int* dims, int cin, int cout, int prec) {
+  Weights W;
+  if (fill_dims(&W, n_layers, dims, cin, cout, prec) != NNCONV_OK) return 0;
+  return layout_weights(&W).bytes;
+}
+
+int weights_prepare(Weights* W, int n_layers, const int* dims, int cin, int cout, int prec,
+                    const float* const* Wsrc, const float* const* bsrc, void* buf, size_t buf_bytes,
+                    cudaStream_t st) {
+  int s = fill_dims(W, n_layers, dims, cin, cout, prec);
+  if (s != NNCONV_OK) return s;
+  WeightsLayout L = layout_weights(W);
+  NNC_REQUIRE(buf != nullptr && L.bytes <= buf_bytes, NNCONV_ERR_WORKSPACE, "weights buffer too small (need %zu)", L.bytes);
+  char* base = static_cast<char*>(buf);
+  const int nl = n_layers;
+  if (nl >= 2) {
+    float* W1 = reinterpret_cast<float*>(base + L.off_W1);
+    float* b1 = reinterpret_cast<float*>(base + L.off_b1);
+    s = launch_pad_convert(PREC_FP32, Wsrc[0], dims[1], dims[0], W1, W->kp[1], dims[0], st);
+    if (s) return s;
+    s = launch_pad_convert(PREC_FP32, bsrc[0], 1, dims[1], b1, 1, W->kp[1], st);
+    if (s) return s;
+    W->W1 = W1;
+    W->b1 = b1;
+  }
+  for (int l = 2; l <= nl - 1; ++l) {
+    void* Wh = base + L.off_Wh[l];
+    float* bh = reinterpret_cast<float*>(base + L.off_bh[l]);
+    s = launch_pad_convert(prec, Wsrc[l - 1], dims[l], dims[l - 1], Wh, W->kp[l], W->kp[l - 1], st);
+    if (s) return s;
+    s = launch_pad_convert(PREC_FP32, bsrc[l - 1], 1, dims[l], bh, 1, W->kp[l], st);
+    if (s) return s;
+    W->Wh[l] = Wh;
+    W->bh[l] = bh;
+  }
+  void* W3p = base + L.off_W3p;
+  float* B3 = reinterpret_cast<float*>(base + L.off_B3);
+  s = launch_w3p(prec, Wsrc[nl - 1], cin, cout, W->K, W->Kp, W->cin_p, W3p, st);
+  if (s) return s;
+  s = launch_pad_convert(PREC_FP32, bsrc[nl - 1], 1, cin * cout, B3, 1, cin * cout, st);
+  if (s) return s;
+  W->W3p = W3p;
+  W->B3 = B3;
+  return NNCONV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// edge features: h_last for every (source-sorted) edge
+// ------------------------------------------------------------------------------------------------
+static int max_hidden_kp(const Weights* W) {
+  int m = 64;
+  for (int l = 1; l <= W->n_layers - 1; ++l) m = W->kp[l] > m ? W->kp[l] : m;
+  return m;
+}
+
+size_t edge_features_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes) {
+  if (W->n_layers <= 2) return 1024;   // h_last is written directly by the first-layer kernel
+  const size_t row = 2 * static_cast<size_t>(max_hidden_kp(W)) * W->esize;   // ping + pong
+  size_t rows_all = static_cast<size_t>(round_up64(P->E > 0 ? P->E : 1, 128));
+  size_t rows = want_bytes / row;
+  rows = rows / 128 * 128;
+  if (rows < 128) rows = 128;
+  if (rows > rows_all) rows = rows_all;
+  return rows * row + 2048;
+}
+
+int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void* h, void* ws, size_t ws_bytes,
+                  cudaStream_t st, int64_t* launches) {
+  const int64_t E = P->E;
+  if (E == 0) return NNCONV_OK;
+  const int nl = W->n_layers;
+  const bool tc = tc_shapes_supported(W);
+  NNC_REQUIRE(tc || W->prec == PREC_FP32, NNCONV_ERR_UNSUPPORTED,
+              "shape not supported by the tensor-core path (out=%d, K=%d); use precision fp32", W->cout, W->K);
+  int s;
+  if (nl == 1) {   // single Linear: h_last = edge_attr (padded)
+    ProfScope ps(PK_LAYER1, st);
+    s = launch_edge_layer1(W->prec, edge_attr, P->perm, 0, E, W->dims[0], nullptr, nullptr, W->Kp, 1, h, st);
+    if (launches) ++*launches;
+    return s;
+  }
+  if (nl == 2) {   // h_last = relu(Linear_1)
+    ProfScope ps(PK_LAYER1, st);
+    s = launch_edge_layer1(W->prec, edge_attr, P->perm, 0, E, W->dims[0], W->W1, W->b1, W->kp[1], 0, h, st);
+    if (launches) ++*launches;
+    return s;
+  }
+  const size_t row = static_cast<size_t>(max_hidden_kp(W)) * W->esize;
+  NNC_REQUIRE(ws != nullptr && ws_bytes >= 2 * 128 * row + 2048, NNCONV_ERR_WORKSPACE, "edge_features: workspace too small");
+  int64_t rows = static_cast<int64_t>((ws_bytes - 2048) / (2 * row)) / 128 * 128;
+  char* bufA = static_cast<char*>(ws);
+  char* bufB = bufA + round_up64(static_cast<int64_t>(rows * row), 1024);
+  for (int64_t e0 = 0; e0 < E; e0 += rows) {
+    const int64_t n = (E - e0) < rows ? (E - e0) : rows;
+    {
+      ProfScope ps(PK_LAYER1, st);
+      s = launch_edge_layer1(W->prec, edge_attr, P->perm, e0, n, W->dims[0], W->W1, W->b1, W->kp[1], 0, bufA, st);
+    }
+    if (s) return s;
+    if (launches) ++*launches;
+    char* cur = bufA;
+    char* nxt = bufB;
+    for (int l = 2; l <= nl - 1; ++l) {
+      const bool last = l == nl - 1;
+      void* dst = last ? static_cast<void*>(static_cast<char*>(h) + static_cast<size_t>(e0) * W->Kp * W->esize)
+                       : static_cast<void*>(nxt);
+      ProfScope ps(PK_HIDDEN_GEMM, st);
+      if (W->prec == PREC_FP32) {
+        s = launch_sgemm_store(reinterpret_cast<const float*>(cur), W->kp[l - 1],
+                               reinterpret_cast<const float*>(W->Wh[l]), W->kp[l - 1], static_cast<float*>(dst),
+                               W->kp[l], static_cast<int>(n), W->kp[l], W->kp[l - 1], W->bh[l], st);
+      } else {
+        s = launch_gemm_tc(W->prec, cur, n, 0, static_cast<int>(n), W->kp[l - 1], W->Wh[l], W->kp[l], W->bh[l], 1,
+                           dst, W->kp[l], st);
+      }
+      if (s) return s;
+      if (launches) ++*launches;
+      char* tmp = cur; cur = nxt; nxt = tmp;
+    }
+  }
+  return NNCONV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one conv application
+// ------------------------------------------------------------------------------------------------
+struct ApplyLayout {
+  size_t off_Xc, off_cvec, off_Y, fixed_bytes, per_node;
+};
+
+static ApplyLayout layout_apply(const Plan* P, const Weights* W) {
+  Carver c(nullptr, ~size_t(0));
+  ApplyLayout L{};
+  const size_t S = P->n_src > 0 ? P->n_src : 1;
+  L.off_Xc = c.off; c.take<char>((S + 128) * W->cin_p * W->esize);
+  L.off_cvec = c.off; c.take<float>(S * W->cout);
+  L.off_Y = c.off;
+  L.fixed_bytes = c.off;
+  L.per_node = static_cast<size_t>(W->cout) * W->Kp * W->esize;
+  return L;
+}
+
+size_t apply_ws_bytes(const Plan* P, const Weights* W, size_t want_y_bytes) {
+  ApplyLayout L = layout_apply(P, W);
+  size_t nodes = want_y_bytes / L.per_node;
+  if (nodes < 1) nodes = 1;
+  if (nodes > static_cast<size_t>(P->n_src > 0 ? P->n_src : 1)) nodes = P->n_src > 0 ? P->n_src : 1;
+  return L.fixed_bytes + nodes * L.per_node + 1024;
+}
+
+int apply(const Plan* P, const Weights* W, const void* h, const float* x, const float* root, const float* bias,
+          int aggr_mean, float* out, void* ws, size_t ws_bytes, cudaStream_t st, int64_t* launches) {
+  int s;
+  {
+    ProfScope ps(PK_NODE_PREP, st);
+    s = launch_out_init(x, root, bias, P->N, W->cin, W->cout, out, st);
+  }
+  if (s) return s;
+  if (launches) ++*launches;
+  if (P->E == 0 || P->n_src == 0) return NNCONV_OK;
+  const bool tc = tc_shapes_supported(W);
+  NNC_REQUIRE(tc || W->prec == PREC_FP32, NNCONV_ERR_UNSUPPORTED,
+              "shape not supported by the tensor-core path (out=%d, K=%d); use precision fp32", W->cout, W->K);
+  ApplyLayout L = layout_apply(P, W);
+  NNC_REQUIRE(ws != nullptr && ws_bytes >= L.fixed_bytes + L.per_node, NNCONV_ERR_WORKSPACE,
+              "apply: workspace too small (need >= %zu bytes)", L.fixed_bytes + L.per_node);
+  char* base = static_cast<char*>(ws);
+  void* Xc = base + L.off_Xc;
+  float* cvec = reinterpret_cast<float*>(base + L.off_cvec);
+  void* Y = base + L.off_Y;
+  int64_t nb_max = static_cast<int64_t>((ws_bytes - L.fixed_bytes) / L.per_node);
+  if (nb_max > P->n_src) nb_max = P->n_src;
+  {
+    ProfScope ps(PK_NODE_PREP, st);
+    s = launch_src_prep(W->prec, x, P->src_nodes, P->n_src, W->cin, W->cin_p, W->cout, W->B3, Xc, cvec, st);
+  }
+  if (s) return s;
+  if (launches) ++*launches;
+  // tile_ptr lives on the device; tile ranges per batch are derived on the host from a small mirror
+  // kept in the plan handle (see nnconv_plan_create).
+  const int* h_tile_ptr = P->h_tile_ptr;
+  const int NY = W->cout * W->Kp;
+  for (int64_t c0 = 0; c0 < P->n_src; c0 += nb_max) {
+    const int nb = static_cast<int>((P->n_src - c0) < nb_max ? (P->n_src - c0) : nb_max);
+    const int tb = h_tile_ptr[c0], te = h_tile_ptr[c0 + nb];
+    {
+      ProfScope ps(PK_Y_GEMM, st);
+      if (W->prec == PREC_FP32)
+        s = launch_sgemm_store(reinterpret_cast<const float*>(Xc) + c0 * W->cin_p, W->cin_p,
+                               reinterpret_cast<const float*>(W->W3p), W->cin_p, static_cast<float*>(Y), NY, nb, NY,
+                               W->cin_p, nullptr, st);
+      else
+        s = launch_gemm_tc(W->prec, Xc, P->n_src, c0, nb, W->cin_p, W->W3p, NY, nullptr, 0, Y, NY, st);
+    }
+    if (s) return s;
+    {
+      ProfScope ps(PK_CONV, st);
+      if (W->prec == PREC_FP32)
+        s = launch_sgemm_scatter(P, static_cast<const float*>(h), W->Kp, static_cast<const float*>(Y), W->cout, tb,
+                                 te, static_cast<int>(c0), cvec, aggr_mean, out, st);
+      else
+        s = launch_conv_tc(W->prec, P, h, W->Kp, Y, nb, W->cout, tb, te, static_cast<int>(c0), cvec, aggr_mean, out,
+                           st);
+    }
+    if (s) return s;
+    if (launches) *launches += 2;
+  }
+  return NNCONV_OK;
+}
+
+}  // namespace nnc
+
+// ==================================================================================================
+// extern "C"
+// ==================================================================================================
+using namespace nnc;
+
+struct nnconv_plan {
+  Plan p;
+  int* h_tile_ptr_storage;
+};
+struct nnconv_weights {
+  Weights w;
+};
+
+extern "C" {
+
+const char* nnconv_last_error(void) { return nnc::g_err; }
+
+int nnconv_abi_version(void) { return NNCONV_B200_ABI_VERSION; }
+
+int nnconv_init(void) { return tc_init(); }
+
+int nnconv_plan_sizes(int64_t E, int64_t N, size_t* ws_bytes, size_t* tmp_bytes) {
+  NNC_REQUIRE(ws_bytes && tmp_bytes, NNCONV_ERR_ARG, "null output pointer");
+  NNC_REQUIRE(E >= 0 && N >= 1, NNCONV_ERR_ARG, "need E >= 0, N >= 1");
+  plan_sizes(E, N, ws_bytes, tmp_bytes);
+  return NNCONV_OK;
+}
+
+int nnconv_plan_create(const int64_t* row0, const int64_t* row1, int64_t E, int64_t N, int flow, void* ws, size_t ws_bytes,
+                       void* tmp, size_t tmp_bytes, void* stream, nnconv_plan_t** out) {
+  NNC_REQUIRE(out != nullptr, NNCONV_ERR_ARG, "null output pointer");
+  *out = nullptr;
+  nnconv_plan* h = new (std::nothrow) nnconv_plan();
+  NNC_REQUIRE(h != nullptr, NNCONV_ERR_ARG, "out of host memory");
+  h->h_tile_ptr_storage = nullptr;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int s = plan_build(&h->p, row0, row1, E, N, flow, ws, ws_bytes, tmp, tmp_bytes, st);
+  if (s != NNCONV_OK) { delete h; return s; }
+  // host mirror of tile_ptr (S+1 ints) so that batch tile ranges need no device read later
+  const int S = h->p.n_src;
+  h->h_tile_ptr_storage = new (std::nothrow) int[static_cast<size_t>(S) + 1];
+  if (!h->h_tile_ptr_storage) { delete h; set_error("out of host memory"); return NNCONV_ERR_ARG; }
+  cudaError_t e = cudaMemcpyAsync(h->h_tile_ptr_storage, h->p.tile_ptr, (static_cast<size_t>(S) + 1) * sizeof(int),
+                                  cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    set_error("plan: copying tile_ptr failed: %s", cudaGetErrorString(e));
+    delete[] h->h_tile_ptr_storage;
+    delete h;
+    return NNCONV_ERR_CUDA;
+  }
+  h->p.h_tile_ptr = h->h_tile_ptr_storage;
+  *out = h;
+  return NNCONV_OK;
+}
+
+void nnconv_plan_destroy(nnconv_plan_t* plan) {
+  if (!plan) return;
+  delete[] plan->h_tile_ptr_storage;
+  delete plan;
+}
+
+int nnconv_plan_info(const nnconv_plan_t* plan, int64_t* info, int n_info) {
+  NNC_REQUIRE(plan && info && n_info >= 7, NNCONV_ERR_ARG, "plan_info: need a plan and >= 7 slots");
+  info[0] = plan->p.E;
+  info[1] = plan->p.N;
+  info[2] = plan->p.n_src;
+  info[3] = plan->p.n_tiles;
+  info[4] = plan->p.max_out_deg;
+  info[5] = plan->p.src_sorted;
+  info[6] = plan->p.flow;
+  return NNCONV_OK;
+}
+
+int nnconv_weights_sizes(int n_layers, const int* dims, int in_channels, int out_channels, int precision,
+                         size_t* bytes) {
+  NNC_REQUIRE(bytes && dims, NNCONV_ERR_ARG, "null pointer");
+  Weights W;
+  int s = fill_dims(&W, n_layers, dims, in_channels, out_channels, precision);
+  if (s) return s;
+  *bytes = layout_weights(&W).bytes;
+  return NNCONV_OK;
+}
+
+int nnconv_weights_create(int n_layers, const int* dims, int in_channels, int out_channels, int precision,
+                          const float* const* W, const float* const* b, void* buf, size_t buf_bytes, void* stream,
+                          nnconv_weights_t** out) {
+  NNC_REQUIRE(out && dims && W && b, NNCONV_ERR_ARG, "null pointer");
+  *out = nullptr;
+  nnconv_weights* h = new (std::nothrow) nnconv_weights();
+  NNC_REQUIRE(h != nullptr, NNCONV_ERR_ARG, "out of host memory");
+  int s = weights_prepare(&h->w, n_layers, dims, in_channels, out_channels, precision, W, b, buf, buf_bytes,
+                          static_cast<cudaStream_t>(stream));
+  if (s != NNCONV_OK) { delete h; return s; }
+  *out = h;
+  return NNCONV_OK;
+}
+
+void nnconv_weights_destroy(nnconv_weights_t* w) { delete w; }
+
+int nnconv_weights_tc_supported(const nnconv_weights_t* w) { return w && tc_shapes_supported(&w->w) ? 1 : 0; }
+
+int nnconv_edge_features_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t want_ws_bytes,
+                               size_t* h_bytes, size_t* ws_bytes) {
+  NNC_REQUIRE(plan && w && h_bytes && ws_bytes, NNCONV_ERR_ARG, "null pointer");
+  const int64_t rows = round_up64(plan->p.E > 0 ? plan->p.E : 1, 128);
+  *h_bytes = static_cast<size_t>(rows) * w->w.Kp * w->w.esize;
+  *ws_bytes = edge_features_ws_bytes(&plan->p, &w->w, want_ws_bytes);
+  return NNCONV_OK;
+}
+
+int nnconv_edge_features(const nnconv_plan_t* plan, const nnconv_weights_t* w, const float* edge_attr, void* h,
+                         void* ws, size_t ws_bytes, void* stream, int64_t* launches) {
+  NNC_REQUIRE(plan && w && (edge_attr || plan->p.E == 0) && h, NNCONV_ERR_ARG, "null pointer");
+  return edge_features(&plan->p, &w->w, edge_attr, h, ws, ws_bytes, static_cast<cudaStream_t>(stream), launches);
+}
+
+int nnconv_apply_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t want_y_bytes, size_t* ws_bytes) {
+  NNC_REQUIRE(plan && w && ws_bytes, NNCONV_ERR_ARG, "null pointer");
+  *ws_bytes = apply_ws_bytes(&plan->p, &w->w, want_y_bytes);
+  return NNCONV_OK;
+}
+
+int nnconv_apply(const nnconv_plan_t* plan, const nnconv_weights_t* w, const void* h, const float* x,
+                 const float* root, const float* bias, int aggr, float* out, void* ws, size_t ws_bytes, void* stream,
+                 int64_t* launches) {
+  NNC_REQUIRE(plan && w && x && out && (h || plan->p.E == 0), NNCONV_ERR_ARG, "null pointer");
+  NNC_REQUIRE(aggr == NNCONV_AGGR_ADD || aggr == NNCONV_AGGR_MEAN, NNCONV_ERR_UNSUPPORTED,
+              "aggr must be add (0) or mean (1); 'max' is used by no call site of the reference and is not built");
+  return apply(&plan->p, &w->w, h, x, root, bias, aggr == NNCONV_AGGR_MEAN, out, ws, ws_bytes,
+               static_cast<cudaStream_t>(stream), launches);
+}
+
+int nnconv_profile_begin(void) {
+  for (auto& r : nnc::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  nnc::g_prof.clear();
+  nnc::g_prof_on = true;
+  return NNCONV_OK;
+}
+
+int nnconv_profile_end(double* ms_by_kind, int64_t* launches_by_kind, int n_kinds) {
+  nnc::g_prof_on = false;
+  NNC_REQUIRE(ms_by_kind && launches_by_kind && n_kinds >= PK_COUNT, NNCONV_ERR_ARG, "profile_end: need >= %d slots", (int)PK_COUNT);
+  NNC_CHECK_CUDA(cudaDeviceSynchronize());
+  for (int k = 0; k < n_kinds; ++k) { ms_by_kind[k] = 0.0; launches_by_kind[k] = 0; }
+  for (auto& r : nnc::g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { ms_by_kind[r.kind] += ms; launches_by_kind[r.kind] += 1; }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  nnc::g_prof.clear();
+  return NNCONV_OK;
+}
+
+int nnconv_gemm_16b(int precision, const void* A, int64_t M, int K, const void* B, int N, const float* bias,
+                    int relu, void* C, void* stream) {
+  NNC_REQUIRE(A && B && C && M >= 1 && M < (int64_t(1) << 31), NNCONV_ERR_ARG, "gemm: bad arguments");
+  return launch_gemm_tc(precision, A, M, 0, static_cast<int>(M), K, B, N, bias, relu, C, N,
+                        static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+// tcgen05 GEMM for the dense stages of the NNConv path (sm_100a only):
+//     C[M, N] (fp16/bf16) = act( A[M, K] * B[N, K]^T + bias )          fp32 accumulation in TMEM
+// used for (a) the hidden layers of the edge MLP (graph-neural-operator/utilities.py:223-227,
+// Linear + ReLU) over a chunk of edges and (b) the per-source matrices
+// Y[c, (o,k)] = sum_i x[c, i] * W_L[i*out + o, k]  (the last Linear reassociated, nn_conv.py:274-275).
+//
+// Structure: persistent CTAs (grid = #SMs), 6 warps: warp 0 = TMA producer (one lane), warp 1 = MMA
+// issuer (one lane) + TMEM allocator, warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU -> 16-bit
+// -> global).  Operands are K-major 128B-swizzled tiles [128 x 64] / [BLOCK_N x 64] staged by TMA in a
+// ring of kStages; accumulators are double buffered in TMEM (2 x BLOCK_N columns) so the epilogue of
+// tile i overlaps the MMAs of tile i+1.
+#include "kernels.h"
+#include "tc05.cuh"
+#include "tmap.h"
+
+namespace nnc {
+
+namespace {
+
+using namespace tc05;
+
+struct GemmTcArgs {
+  int M, N, K;
+  int a_row0;          // first row of A inside the tensor map
+  const float* bias;   // [N] or nullptr
+  int relu;
+  void* C;
+  int64_t ldc;         // elements
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kBlockM = 128;
+  static constexpr int kBlockK = 64;
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+  static constexpr int kTmemCols = 2 * BLOCK_N;   // power of two >= 32 for BLOCK_N in {64,128,256}
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N, int FMT>
+__global__ void __launch_bounds__(192, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmTcArgs a) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::kStages;
+  uint64_t* tfull = bars + 2 * Cfg::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int m_blocks = ceil_div(a.M, Cfg::kBlockM);
+  const int n_blocks = ceil_div(a.N, BLOCK_N);
+  const int num_tiles = m_blocks * n_blocks;
+  const int num_kb = a.K / Cfg::kBlockK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);   // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int mb = t / n_blocks, nb = t % n_blocks;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+          tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full[stage], kb * Cfg::kBlockK,
+                      a.a_row0 + mb * Cfg::kBlockM, kEvictNormal);
+          tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full[stage], kb * Cfg::kBlockK, nb * BLOCK_N,
+                      kEvictLast);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = idesc_f16(FMT, Cfg::kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1u);
+        fence_after_sync();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          fence_after_sync();
+          const uint64_t adesc = smem_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+          const uint64_t bdesc = smem_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+          for (int k = 0; k < Cfg::kBlockK / 16; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128B swizzle span: +2 in 16-byte units
+            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);           // frees the smem slot once these MMAs have read it
+          if (kb == num_kb - 1) umma_commit(&tfull[as]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps 2..5
+    const int quarter = warp % 4;     // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int mb = t / n_blocks, nb = t % n_blocks;
+      const int as = it & 1;
+      mbar_wait(&tfull[as], (it >> 1) & 1);
+      fence_after_sync();
+      const int row = mb * Cfg::kBlockM + quarter * 32 + lane;
+      const bool row_ok = row < a.M;
+      uint16_t* crow = reinterpret_cast<uint16_t*>(a.C) + static_cast<int64_t>(row) * a.ldc;
+#pragma unroll 1
+      for (int cc = 0; cc < BLOCK_N / 32; ++cc) {
+        const int col0 = nb * BLOCK_N + cc * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N + cc * 32, v);
+        tmem_ld_wait();
+        if (col0 < a.N && row_ok) {
+          uint32_t packed[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
+            if (a.bias) {
+              f0 += __ldg(a.bias + col0 + 2 * j);
+              f1 += __ldg(a.bias + col0 + 2 * j + 1);
+            }
+            if (a.relu) {
+              f0 = fmaxf(f0, 0.f);
+              f1 = fmaxf(f1, 0.f);
+            }
+            if (FMT == 0) {
+              __half2 h = __floats2half2_rn(f0, f1);
+              packed[j] = *reinterpret_cast<uint32_t*>(&h);
+            } else {
+              __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+              packed[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+          }
+          uint4* dst = reinterpret_cast<uint4*>(crow + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+int g_num_sms = 0;
+
+template <int BLOCK_N, int FMT>
+int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& a, cudaStream_t st) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NNC_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int tiles = ceil_div(a.M, 128) * ceil_div(a.N, BLOCK_N);
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  k_gemm_tc<BLOCK_N, FMT><<<grid, 192, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
+}
+
+}  // namespace
+
+int tc_init() {
+  if (g_num_sms > 0) return NNCONV_OK;
+  int dev = 0;
+  NNC_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  NNC_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  NNC_REQUIRE(prop.major == 10, NNCONV_ERR_UNSUPPORTED,
+              "libnnconv_b200 needs an sm_100-class GPU (found sm_%d%d)", prop.major, prop.minor);
+  int s = tmap_init();
+  if (s != NNCONV_OK) return s;
+  g_num_sms = prop.multiProcessorCount;
+  return NNCONV_OK;
+}
+
+int tc_num_sms() { return g_num_sms; }
+
+int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a_row0, int M, int K, const void* B,
+                   int N, const float* bias, int relu, void* C, int64_t ldc, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return NNCONV_OK;
+  int s = tc_init();
+  if (s != NNCONV_OK) return s;
+  NNC_REQUIRE(prec == PREC_F16 || prec == PREC_BF16, NNCONV_ERR_ARG, "gemm_tc: 16-bit precisions only");
+  NNC_REQUIRE(K % 64 == 0 && N % 64 == 0 && K >= 64, NNCONV_ERR_ARG, "gemm_tc: K=%d N=%d must be multiples of 64", K, N);
+  NNC_REQUIRE(ldc % 8 == 0, NNCONV_ERR_ARG, "gemm_tc: ldc must be a multiple of 8 elements");
+  const int bf = prec == PREC_BF16;
+  const int BN = (N % 256 == 0 || N > 256) ? 256 : (N % 128 == 0 || N > 128) ? 128 : 64;
+  CUtensorMap tmA, tmB;
+  s = make_tmap_2d_16b(&tmA, bf, A_base, static_cast<uint64_t>(a_rows_total), static_cast<uint64_t>(K), 128);
+  if (s != NNCONV_OK) return s;
+  s = make_tmap_2d_16b(&tmB, bf, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), BN);
+  if (s != NNCONV_OK) return s;
+  GemmTcArgs a;
+  a.M = M; a.N = N; a.K = K; a.a_row0 = static_cast<int>(a_row0); a.bias = bias; a.relu = relu; a.C = C; a.ldc = ldc;
+  if (BN == 256) return bf ? launch_gemm_cfg<256, 1>(tmA, tmB, a, st) : launch_gemm_cfg<256, 0>(tmA, tmB, a, st);
+  if (BN == 128) return bf ? launch_gemm_cfg<128, 1>(tmA, tmB, a, st) : launch_gemm_cfg<128, 0>(tmA, tmB, a, st);
+  return bf ? launch_gemm_cfg<64, 1>(tmA, tmB, a, st) : launch_gemm_cfg<64, 0>(tmA, tmB, a, st);
+}
+
+}  // namespace nnc

@@ -1,0 +1,333 @@
+// CUDA-core kernels of the NNConv path:
+//   * parameter preparation (pad / convert / permute the last Linear layer into W3p)
+//   * first edge-MLP layer (k_in is 4..6: no tensor-core shape) fused with the edge permutation
+//   * per-node prologue: out = x@root + bias, compact fp16 copy of x, c = x @ B3
+//   * a plain fp32 NT-GEMM with three epilogues: the PREC_FP32 path (any shape) of the hidden layers,
+//     the per-source matrices Y and the per-edge contraction + scatter.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace nnc {
+
+namespace {
+
+template <typename T>
+__device__ __forceinline__ T cvt(float v);
+template <>
+__device__ __forceinline__ float cvt<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half cvt<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 cvt<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// dst[Rp x Cp] (T) <- src[R x C] fp32, zero padded
+template <typename T>
+__global__ void k_pad_convert(const float* __restrict__ src, int R, int C, T* __restrict__ dst, int Rp, int Cp) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<int64_t>(Rp) * Cp) return;
+  int r = static_cast<int>(i / Cp), c = static_cast<int>(i % Cp);
+  float v = (r < R && c < C) ? src[static_cast<int64_t>(r) * C + c] : 0.f;
+  dst[i] = cvt<T>(v);
+}
+
+// W3p[(o*Kp + k) * cin_p + i] = W_L[(i*cout + o) * K + k]   (W_L is the last Linear: [cin*cout, K])
+template <typename T>
+__global__ void k_w3p(const float* __restrict__ WL, int cin, int cout, int K, int Kp, int cin_p, T* __restrict__ dst) {
+  int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  int64_t total = static_cast<int64_t>(cout) * Kp * cin_p;
+  if (idx >= total) return;
+  int i = static_cast<int>(idx % cin_p);
+  int64_t ok = idx / cin_p;
+  int k = static_cast<int>(ok % Kp);
+  int o = static_cast<int>(ok / Kp);
+  float v = (i < cin && k < K) ? WL[(static_cast<int64_t>(i) * cout + o) * K + k] : 0.f;
+  dst[idx] = cvt<T>(v);
+}
+
+// First layer: h1[p, j] = relu(b1[j] + sum_c W1[j, c] * edge_attr[perm[p], c]),  j < kp1 (pad rows of W1/b1 are 0)
+// identity (single-Linear MLP): h[p, j] = edge_attr[perm[p], j] (zero padded), no ReLU.
+constexpr int kL1Edges = 32;
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_edge_layer1(const float* __restrict__ edge_attr, const int* __restrict__ perm, int64_t e_begin, int64_t e_count,
+              int k_in, const float* __restrict__ W1, const float* __restrict__ b1, int kp1, int identity,
+              T* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* s_ea = sm;                       // [kL1Edges][k_in]
+  int64_t p0 = static_cast<int64_t>(blockIdx.x) * kL1Edges;
+  int64_t rem = e_count - p0;
+  int ne = rem < kL1Edges ? static_cast<int>(rem) : kL1Edges;
+  for (int i = threadIdx.x; i < ne * k_in; i += blockDim.x) {
+    int e = i / k_in, c = i % k_in;
+    int64_t p = e_begin + p0 + e;
+    int64_t src = perm ? perm[p] : p;
+    s_ea[i] = edge_attr[src * k_in + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < kp1; j += blockDim.x) {
+    if (identity) {
+      for (int e = 0; e < ne; ++e)
+        out[(p0 + e) * kp1 + j] = cvt<T>(j < k_in ? s_ea[e * k_in + j] : 0.f);
+      continue;
+    }
+    float w[16];
+    const bool small = k_in <= 16;
+    if (small) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) w[c] = c < k_in ? W1[static_cast<int64_t>(j) * k_in + c] : 0.f;
+    }
+    float bj = b1[j];
+    for (int e = 0; e < ne; ++e) {
+      float acc = bj;
+      if (small) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (c < k_in) acc = fmaf(w[c], s_ea[e * k_in + c], acc);
+      } else {
+        for (int c = 0; c < k_in; ++c) acc = fmaf(W1[static_cast<int64_t>(j) * k_in + c], s_ea[e * k_in + c], acc);
+      }
+      out[(p0 + e) * kp1 + j] = cvt<T>(fmaxf(acc, 0.f));
+    }
+  }
+}
+
+// out[n, o] = bias[o] + sum_i x[n, i] root[i, o]   (graph-neural-operator/nn_conv.py:277-282), or 0
+__global__ void k_out_init(const float* __restrict__ x, const float* __restrict__ root, const float* __restrict__ bias,
+                           int64_t N, int cin, int cout, float* __restrict__ out) {
+  extern __shared__ float sx[];   // [nodes_per_block][cin]
+  const int npb = blockDim.y;
+  int64_t n = static_cast<int64_t>(blockIdx.x) * npb + threadIdx.y;
+  float* myx = sx + threadIdx.y * cin;
+  if (root != nullptr && n < N)
+    for (int i = threadIdx.x; i < cin; i += blockDim.x) myx[i] = x[n * cin + i];
+  __syncthreads();
+  if (n >= N) return;
+  for (int o = threadIdx.x; o < cout; o += blockDim.x) {
+    float acc = bias ? bias[o] : 0.f;
+    if (root)
+      for (int i = 0; i < cin; ++i) acc = fmaf(myx[i], root[i * cout + o], acc);
+    out[n * cout + o] = acc;
+  }
+}
+
+// per compact source c: Xc[c, :] = x[src_nodes[c], :] (converted, zero padded to cin_p),
+//                       cvec[c, o] = sum_i x[n, i] * B3[i, o]       (bias of the last Linear, reassociated)
+template <typename T>
+__global__ void k_src_prep(const float* __restrict__ x, const int* __restrict__ src_nodes, int S, int cin, int cin_p,
+                           int cout, const float* __restrict__ B3, T* __restrict__ Xc, float* __restrict__ cvec) {
+  extern __shared__ float sx[];
+  const int npb = blockDim.y;
+  int c = blockIdx.x * npb + threadIdx.y;
+  float* myx = sx + threadIdx.y * cin;
+  int n = c < S ? src_nodes[c] : 0;
+  if (c < S)
+    for (int i = threadIdx.x; i < cin; i += blockDim.x) myx[i] = x[static_cast<int64_t>(n) * cin + i];
+  __syncthreads();
+  if (c >= S) return;
+  for (int i = threadIdx.x; i < cin_p; i += blockDim.x)
+    Xc[static_cast<int64_t>(c) * cin_p + i] = cvt<T>(i < cin ? myx[i] : 0.f);
+  for (int o = threadIdx.x; o < cout; o += blockDim.x) {
+    float acc = 0.f;
+    for (int i = 0; i < cin; ++i) acc = fmaf(myx[i], B3[i * cout + o], acc);
+    cvec[static_cast<int64_t>(c) * cout + o] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 NT GEMM, 64x64x16 tiles, 256 threads, 4x4 register blocking.   C = A[M,K] * B[N,K]^T
+// ------------------------------------------------------------------------------------------------
+enum { EPI_STORE = 0, EPI_BIAS_RELU = 1, EPI_SCATTER = 2 };
+
+struct SgemmArgs {
+  const float* A;
+  int64_t lda;
+  const float* B;
+  int64_t ldb;
+  float* C;
+  int64_t ldc;
+  int M, N, K;
+  const float* bias;   // EPI_BIAS_RELU
+  // EPI_SCATTER (grid.x = tile): A rows = h rows of the tile, B = Y of the tile's source
+  const int *tile_c, *tile_e0, *tile_cnt, *dst_sorted;
+  const float *inv_deg, *cvec;
+  int tile_begin, c0;
+  int64_t y_stride;    // elements between consecutive sources in Y
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(256) k_sgemm_nt(SgemmArgs a) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const float* A = a.A;
+  const float* B = a.B;
+  int M = a.M;
+  int n0 = blockIdx.y * 64;
+  int c = 0, e0 = 0;
+  int m_base = 0;
+  if (EPI == EPI_SCATTER) {
+    int t = a.tile_begin + blockIdx.x / 2;
+    c = a.tile_c[t];
+    e0 = a.tile_e0[t];
+    M = a.tile_cnt[t];
+    m_base = (blockIdx.x % 2) * 64;
+    if (m_base >= M) return;
+    A = a.A + static_cast<int64_t>(e0) * a.lda;
+    B = a.B + static_cast<int64_t>(c - a.c0) * a.y_stride;
+  } else {
+    m_base = blockIdx.x * 64;
+  }
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < a.K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      int r = i / 16, kk = i % 16;
+      int gm = m_base + r, gn = n0 + r, gk = k0 + kk;
+      As[kk][r] = (gm < M && gk < a.K) ? A[static_cast<int64_t>(gm) * a.lda + gk] : 0.f;
+      Bs[kk][r] = (gn < a.N && gk < a.K) ? B[static_cast<int64_t>(gn) * a.ldb + gk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int gm = m_base + ty * 4 + i;
+    if (gm >= M) continue;
+    if (EPI == EPI_SCATTER) {
+      int d = a.dst_sorted[e0 + gm];
+      float sc = a.inv_deg ? a.inv_deg[d] : 1.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int gn = n0 + tx * 4 + j;
+        if (gn < a.N) {
+          float v = (acc[i][j] + a.cvec[static_cast<int64_t>(c) * a.N + gn]) * sc;
+          atomicAdd(&a.C[static_cast<int64_t>(d) * a.ldc + gn], v);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int gn = n0 + tx * 4 + j;
+        if (gn < a.N) {
+          float v = acc[i][j];
+          if (EPI == EPI_BIAS_RELU) v = fmaxf(v + a.bias[gn], 0.f);
+          a.C[static_cast<int64_t>(gm) * a.ldc + gn] = v;
+        }
+      }
+    }
+  }
+}
+
+template <typename T>
+int launch_pad_convert_t(const float* src, int R, int C, void* dst, int Rp, int Cp, cudaStream_t st) {
+  int64_t total = static_cast<int64_t>(Rp) * Cp;
+  if (total == 0) return NNCONV_OK;
+  k_pad_convert<T><<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(src, R, C, static_cast<T*>(dst), Rp, Cp);
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
+}
+
+}  // namespace
+
+int launch_pad_convert(int prec, const float* src, int R, int C, void* dst, int Rp, int Cp, cudaStream_t st) {
+  if (prec == PREC_FP32) return launch_pad_convert_t<float>(src, R, C, dst, Rp, Cp, st);
+  if (prec == PREC_F16) return launch_pad_convert_t<__half>(src, R, C, dst, Rp, Cp, st);
+  return launch_pad_convert_t<__nv_bfloat16>(src, R, C, dst, Rp, Cp, st);
+}
+
+int launch_w3p(int prec, const float* WL, int cin, int cout, int K, int Kp, int cin_p, void* dst, cudaStream_t st) {
+  int64_t total = static_cast<int64_t>(cout) * Kp * cin_p;
+  unsigned g = (unsigned)ceil_div64(total, 256);
+  if (prec == PREC_FP32) k_w3p<float><<<g, 256, 0, st>>>(WL, cin, cout, K, Kp, cin_p, static_cast<float*>(dst));
+  else if (prec == PREC_F16) k_w3p<__half><<<g, 256, 0, st>>>(WL, cin, cout, K, Kp, cin_p, static_cast<__half*>(dst));
+  else k_w3p<__nv_bfloat16><<<g, 256, 0, st>>>(WL, cin, cout, K, Kp, cin_p, static_cast<__nv_bfloat16*>(dst));
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
+}
+
+int launch_edge_layer1(int prec, const float* edge_attr, const int* perm, int64_t e_begin, int64_t e_count, int k_in,
+                       const float* W1, const float* b1, int kp1, int identity, void* out, cudaStream_t st) {
+  if (e_count <= 0) return NNCONV_OK;
+  unsigned g = (unsigned)ceil_div64(e_count, kL1Edges);
+  size_t sm = sizeof(float) * kL1Edges * k_in;
+  if (prec == PREC_FP32)
+    k_edge_layer1<float><<<g, 256, sm, st>>>(edge_attr, perm, e_begin, e_count, k_in, W1, b1, kp1, identity,
+                                             static_cast<float*>(out));
+  else if (prec == PREC_F16)
+    k_edge_layer1<__half><<<g, 256, sm, st>>>(edge_attr, perm, e_begin, e_count, k_in, W1, b1, kp1, identity,
+                                              static_cast<__half*>(out));
+  else
+    k_edge_layer1<__nv_bfloat16><<<g, 256, sm, st>>>(edge_attr, perm, e_begin, e_count, k_in, W1, b1, kp1, identity,
+                                                     static_cast<__nv_bfloat16*>(out));
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
+}
+
+int launch_out_init(const float* x, const float* root, const float* bias, int64_t N, int cin, int cout, float* out,
+                    cudaStream_t st) {
+  dim3 b(64, 4);
+  unsigned g = (unsigned)ceil_div64(N, b.y);
+  k_out_init<<<g, b, sizeof(float) * b.y * cin, st>>>(x, root, bias, N, cin, cout, out);
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
+}
+
+int launch_src_prep(int prec, const float* x, const int* src_nodes, int S, int cin, int cin_p, int cout,
+                    const float* B3, void* Xc, float* cvec, cudaStream_t st) {
+  if (S <= 0) return NNCONV_OK;
+  dim3 b(64, 4);
+  unsigned g = (unsigned)ceil_div(S, (int)b.y);
+  size_t sm = sizeof(float) * b.y * cin;
+  if (prec == PREC_FP32)
+    k_src_prep<float><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3, static_cast<float*>(Xc), cvec);
+  else if (prec == PREC_F16)
+    k_src_prep<__half><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3, static_cast<__half*>(Xc), cvec);
+  else
+    k_src_prep<__nv_bfloat16><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3,
+                                                static_cast<__nv_bfloat16*>(Xc), cvec);
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
+}
+
+int launch_sgemm_store(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
+                       int K, const float* bias_relu, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return NNCONV_OK;
+  SgemmArgs a{};
+  a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K; a.bias = bias_relu;
+  dim3 g(ceil_div(M, 64), ceil_div(N, 64));
+  if (bias_relu) k_sgemm_nt<EPI_BIAS_RELU><<<g, 256, 0, st>>>(a);
+  else k_sgemm_nt<EPI_STORE><<<g, 256, 0, st>>>(a);
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
+}
+
+int launch_sgemm_scatter(const Plan* P, const float* h, int Kp, const float* Y, int cout, int tile_begin, int tile_end,
+                         int c0, const float* cvec, int aggr_mean, float* out, cudaStream_t st) {
+  int nt = tile_end - tile_begin;
+  if (nt <= 0) return NNCONV_OK;
+  SgemmArgs a{};
+  a.A = h; a.lda = Kp; a.B = Y; a.ldb = Kp; a.C = out; a.ldc = cout; a.M = 0; a.N = cout; a.K = Kp;
+  a.tile_c = P->tile_c; a.tile_e0 = P->tile_e0; a.tile_cnt = P->tile_cnt; a.dst_sorted = P->dst_sorted;
+  a.inv_deg = aggr_mean ? P->inv_deg : nullptr; a.cvec = cvec; a.tile_begin = tile_begin; a.c0 = c0;
+  a.y_stride = static_cast<int64_t>(cout) * Kp;
+  dim3 g(nt * 2, ceil_div(cout, 64));
+  k_sgemm_nt<EPI_SCATTER><<<g, 256, 0, st>>>(a);
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
+}
+
+}  // namespace nnc

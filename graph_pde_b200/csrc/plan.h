@@ -1,0 +1,68 @@
+// Internal (C++) view of the opaque handles exported through include/nnconv_b200.h.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace nnc {
+
+constexpr int kMaxLayers = 8;
+
+enum Precision : int { PREC_FP32 = 0, PREC_F16 = 1, PREC_BF16 = 2 };
+
+struct Plan {
+  int64_t E, N;
+  int flow;
+  int n_src;        // S: sources with at least one out-edge (compact index c in [0,S))
+  int n_tiles;      // T: tiles of <= 128 edges, never spanning two sources
+  int max_out_deg;
+  int src_sorted;   // caller's edge list was already grouped by source (perm == identity, not stored)
+  const int* perm;        // [E] sorted position -> original edge id, nullptr = identity
+  const int* dst_sorted;  // [E]
+  const int* src_nodes;   // [S] node id of compact source c
+  const int* group_ptr;   // [S+1] first sorted edge of source c
+  const int* tile_ptr;    // [S+1] first tile of source c
+  const int* tile_c;      // [T]
+  const int* tile_e0;     // [T]
+  const int* tile_cnt;    // [T]
+  const float* inv_deg;   // [N] 1/max(in_degree,1)
+  const int* h_tile_ptr;  // HOST mirror of tile_ptr ([S+1]) owned by the C handle
+};
+
+void plan_sizes(int64_t E, int64_t N, size_t* ws_bytes, size_t* tmp_bytes);
+int plan_build(Plan* P, const int64_t* row0, const int64_t* row1, int64_t E, int64_t N, int flow, void* ws, size_t ws_bytes,
+               void* tmp, size_t tmp_bytes, cudaStream_t st);
+
+// Prepared (padded / permuted / down-converted) snapshot of the edge-MLP parameters.
+struct Weights {
+  int n_layers;                 // Linear layers of the edge MLP (DenseNet)
+  int dims[kMaxLayers + 1];     // k_in, k_1, ..., cin*cout
+  int kp[kMaxLayers + 1];       // padded widths (multiples of 64) of the activations h_1 .. h_{L-1}; kp[0] = k_in
+  int cin, cout, cin_p;
+  int K, Kp;                    // width of the hoisted per-edge feature h_last (= dims[L-1]) and its padding
+  int prec;
+  size_t esize;                 // bytes per element of activations / tensor-core operands
+  const float* W1;              // [kp[1], k_in] fp32 (zero padded rows); nullptr when n_layers == 1
+  const float* b1;              // [kp[1]]
+  const void* Wh[kMaxLayers];   // hidden layers l = 2 .. L-1: [kp[l], kp[l-1]] in `prec`
+  const float* bh[kMaxLayers];  // [kp[l]] fp32
+  const void* W3p;              // [cout*Kp, cin_p] in `prec`:  W3p[(o*Kp + k), i] = W_L[i*cout + o, k]
+  const float* B3;              // [cin, cout] fp32 = b_L viewed (in, out)
+};
+
+size_t weights_bytes(int n_layers, const int* dims, int cin, int cout, int prec);
+int weights_prepare(Weights* W, int n_layers, const int* dims, int cin, int cout, int prec,
+                    const float* const* Wsrc, const float* const* bsrc, void* buf, size_t buf_bytes,
+                    cudaStream_t st);
+
+// edge features: h_last[p, :] for every sorted edge p  (x-independent prefix of the edge MLP)
+size_t edge_features_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes);
+int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void* h, void* ws, size_t ws_bytes,
+                  cudaStream_t st, int64_t* launches);
+
+// one conv application given h_last
+size_t apply_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes);
+int apply(const Plan* P, const Weights* W, const void* h, const float* x, const float* root, const float* bias,
+          int aggr_mean, float* out, void* ws, size_t ws_bytes, cudaStream_t st, int64_t* launches);
+
+}  // namespace nnc

@@ -1,0 +1,76 @@
+"""Input side of the NNConv path: radius ("ball") graphs of a regular square mesh, built without the
+reference's dense O(N^2) distance matrix.
+
+Reference being mirrored: ``SquareMeshGenerator`` (graph-neural-operator/utilities.py:229-285):
+``ball_connectivity(r)`` = ``np.vstack(np.where(pairwise_distances(grid) <= r))`` (:250-255) and
+``attributes(theta=...)`` = ``[pos_src, pos_dst, theta_src, theta_dst]`` (:269-277).  The reference cannot
+build the 241 x 241 graph (27 GB distance matrix); here edges are enumerated per node from the integer
+lattice stencil, on whatever device is asked (torch ops only -- this is input generation, not the hot path).
+
+Edge ORDER is the reference's: source-major, destination ascending (np.where row-major order).
+TIE RULE: lattice offsets whose distance equals r exactly (e.g. (+-12, 0) at s=241, r=0.05)
+are decided in exact integer arithmetic: included when ``ties_in`` (mathematical <=), excluded otherwise;
+sklearn's float64 expanded-form distance decides them by rounding noise.
+"""
+import math
+
+import torch
+
+
+def ball_offsets(s, r, ties_in=True):
+    rr = r * (s - 1)
+    lim2 = rr * rr
+    big = int(math.floor(rr + 1e-9))
+    offs = []
+    for dy in range(-big, big + 1):
+        for dx in range(-big, big + 1):
+            d2 = dx * dx + dy * dy
+            on_sphere = abs(d2 - lim2) <= 1e-9 * max(lim2, 1.0)
+            if (d2 < lim2 and not on_sphere) or (on_sphere and ties_in):
+                offs.append((dy, dx))
+    return offs      # sorted by (dy, dx): ascending destination index for a fixed source
+
+
+def square_grid(s, device='cpu', dtype=torch.float32):
+    """utilities.py:241-248: node = iy*s + ix, position (ix/(s-1), iy/(s-1)) (np.meshgrid 'xy' order)."""
+    lin = torch.linspace(0.0, 1.0, s, dtype=torch.float64, device=device)
+    gy, gx = torch.meshgrid(lin, lin, indexing='ij')
+    return torch.stack([gx.reshape(-1), gy.reshape(-1)], dim=1).to(dtype)
+
+
+def ball_connectivity(s, r, device='cpu', ties_in=True, node_chunk=1 << 16, nodes=None):
+    """edge_index [2, E] int64 on `device`, source-major / destination-ascending.
+    nodes=(n0, n1) restricts the SOURCE nodes to [n0, n1) (used to cut bounded samples of a big graph)."""
+    offs = torch.tensor(ball_offsets(s, r, ties_in), dtype=torch.int64, device=device)   # [K, 2] (dy, dx)
+    n_lo, n = (0, s * s) if nodes is None else (int(nodes[0]), min(int(nodes[1]), s * s))
+    out = []
+    for n0 in range(n_lo, n, node_chunk):
+        node = torch.arange(n0, min(n, n0 + node_chunk), dtype=torch.int64, device=device)
+        iy, ix = node // s, node % s
+        jy = iy[:, None] + offs[None, :, 0]
+        jx = ix[:, None] + offs[None, :, 1]
+        ok = (jy >= 0) & (jy < s) & (jx >= 0) & (jx < s)
+        src = node[:, None].expand_as(jy)[ok]
+        dst = (jy * s + jx)[ok]
+        out.append(torch.stack([src, dst]))
+    return torch.cat(out, dim=1)
+
+
+def ball_edge_attr(grid, edge_index, theta):
+    """utilities.py:269-277: edge_attr[e] = (pos_src(2), pos_dst(2), theta_src, theta_dst), fp32."""
+    src, dst = edge_index[0], edge_index[1]
+    theta = theta.to(grid.dtype)
+    return torch.cat([grid[src], grid[dst], theta[src, None], theta[dst, None]], dim=1).float().contiguous()
+
+
+def darcy_sample(s, r, device='cpu', seed=0, edge_index=None, ties_in=True):
+    """Synthetic Darcy-2D sample with the shapes of UAI1_full_resolution.py:143-159: node features
+    x [N,6] = (grid xy, a, a_smooth, a_gradx, a_grady) ~ N(0,1) stand-ins, edge_attr [E,6]."""
+    g = torch.Generator(device='cpu').manual_seed(seed)
+    grid = square_grid(s, device)
+    feats = torch.randn(s * s, 4, generator=g).to(device)
+    if edge_index is None:
+        edge_index = ball_connectivity(s, r, device, ties_in)
+    x = torch.cat([grid, feats], dim=1).contiguous()
+    edge_attr = ball_edge_attr(grid, edge_index, feats[:, 0])
+    return x, edge_index, edge_attr

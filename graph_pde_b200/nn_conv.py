@@ -1,0 +1,330 @@
+"""B200-native drop-in for the reference's edge-conditioned convolution.
+
+Mirrors the operator interface of the reference (paths relative to neuraloperator/graph-pde):
+
+* ``NNConv_old(in_channels, out_channels, nn, aggr='add', root_weight=True, bias=True, **kwargs)``
+  -- graph-neural-operator/nn_conv.py:197-286 (ctor :234-259, reset_parameters :261-265,
+  forward :267-271, message :273-275, update :277-282, __repr__ :284-286)
+* ``NNConv`` -- the upstream ``torch_geometric.nn.NNConv`` imported by the MGKN scripts
+  (multipole-graph-neural-operator/neurips1_MGKN.py:10,41; same math, same signature).
+
+Same attribute names (``in_channels, out_channels, nn, aggr, root, bias``), same state-dict keys
+(``nn.layers.{0,2,4}.{weight,bias}``, ``root``, ``bias``), same init distributions.  The arithmetic
+runs in libnnconv_b200.so (hand-written sm_100a CUDA, C ABI in include/nnconv_b200.h); PyTorch only
+owns the device memory and the stream.  There is no CPU / eager fallback: a CPU tensor, a missing
+library or an unsupported edge network raises.
+
+Algorithm: the edge MLP minus its last Linear is x-independent, so its output
+``h_e`` is computed once per (edge_attr, parameters) and cached across the T applications of the shared
+conv in KernelNN.forward (graph-neural-operator/UAI1_full_resolution.py:29-30); each application then
+runs ``m_e = h_e . Y_src + c_src`` with the per-source matrix ``Y_src = x_src (x) W_L`` and scatters
+``m_e / deg`` into the target rows.
+"""
+import collections
+import ctypes
+import math
+import os
+import weakref
+
+import torch
+from torch.nn import Parameter
+
+from . import _lib
+
+__all__ = ['NNConv_old', 'NNConv', 'ECConv', 'stats', 'clear_caches', 'default_precision']
+
+stats = {'launches': 0, 'plans_built': 0, 'edge_feature_passes': 0, 'applies': 0, 'weight_preps': 0}
+
+_PLAN_CACHE = collections.OrderedDict()
+_PLAN_CACHE_MAX = int(os.environ.get('NNCONV_B200_PLAN_CACHE', '64'))
+_Y_BYTES = int(os.environ.get('NNCONV_B200_Y_BYTES', str(48 << 20)))       # per-source matrices kept L2 sized
+_EF_WS_BYTES = int(os.environ.get('NNCONV_B200_EF_WS_BYTES', str(1 << 30)))  # hidden-layer ping-pong chunk
+
+
+def default_precision():
+    return os.environ.get('NNCONV_B200_PRECISION', 'f16')
+
+
+def clear_caches():
+    _PLAN_CACHE.clear()
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError('graph_pde_b200.NNConv: `%s` must be a CUDA tensor (there is no CPU path); got %s'
+                           % (name, t.device))
+
+
+class _Plan(object):
+    """Per-edge_index preprocessing owned by the C library (nnconv_plan_t) + the buffers it lives in."""
+
+    def __init__(self, edge_index, n_nodes, flow):
+        L = _lib.lib()
+        _lib.check(L.nnconv_init())
+        e = edge_index.size(1)
+        ws_b, tmp_b = ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(L.nnconv_plan_sizes(e, n_nodes, ctypes.byref(ws_b), ctypes.byref(tmp_b)))
+        dev = edge_index.device
+        self.ws = torch.empty(ws_b.value, dtype=torch.uint8, device=dev)
+        tmp = torch.empty(tmp_b.value, dtype=torch.uint8, device=dev)
+        row0, row1 = edge_index[0], edge_index[1]
+        if row0.stride(0) != 1:
+            row0 = row0.contiguous()
+        if row1.stride(0) != 1:
+            row1 = row1.contiguous()
+        self._rows = (row0, row1)
+        self.edge_index = edge_index          # keeps the storage (and so the cache key) alive
+        h = ctypes.c_void_p()
+        _lib.check(L.nnconv_plan_create(_ptr(row0), _ptr(row1), e, n_nodes, _lib.FLOW[flow], _ptr(self.ws),
+                                        ws_b.value, _ptr(tmp), tmp_b.value, _stream_ptr(dev), ctypes.byref(h)))
+        self.handle = h
+        self.key = _plan_key(edge_index, n_nodes, flow)
+        info = (ctypes.c_int64 * 8)()
+        _lib.check(L.nnconv_plan_info(h, info, 8))
+        self.E, self.N, self.n_src, self.n_tiles, self.max_out_deg, self.src_sorted = [int(v) for v in info[:6]]
+        stats['plans_built'] += 1
+        self._finalizer = weakref.finalize(self, L.nnconv_plan_destroy, h)
+
+
+def _plan_key(edge_index, n_nodes, flow):
+    return (edge_index.data_ptr(), tuple(edge_index.shape), tuple(edge_index.stride()), edge_index._version,
+            edge_index.device.index, int(n_nodes), flow)
+
+
+def get_plan(edge_index, n_nodes, flow='source_to_target'):
+    key = _plan_key(edge_index, n_nodes, flow)
+    plan = _PLAN_CACHE.get(key)
+    if plan is not None:
+        _PLAN_CACHE.move_to_end(key)
+        return plan
+    plan = _Plan(edge_index, n_nodes, flow)
+    _PLAN_CACHE[key] = plan
+    while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
+        _PLAN_CACHE.popitem(last=False)
+    return plan
+
+
+def _linear_chain(nn_module):
+    """The edge network must be the reference's DenseNet shape: Linear (ReLU Linear)* with no output
+    nonlinearity (graph-neural-operator/utilities.py:201-227; every call site passes torch.nn.ReLU,
+    normalize=False)."""
+    mods = [m for m in nn_module.modules() if len(list(m.children())) == 0]
+    lin = []
+    expect_linear = True
+    for m in mods:
+        if isinstance(m, torch.nn.Linear):
+            if not expect_linear:
+                raise NotImplementedError('edge network: two Linear layers without a ReLU in between')
+            if m.bias is None:
+                raise NotImplementedError('edge network: Linear without bias is not supported')
+            lin.append(m)
+            expect_linear = False
+        elif isinstance(m, torch.nn.ReLU):
+            if expect_linear:
+                raise NotImplementedError('edge network: ReLU must follow a Linear layer')
+            expect_linear = True
+        else:
+            raise NotImplementedError('edge network: only Linear/ReLU chains (DenseNet) are supported, found %s'
+                                      % type(m).__name__)
+    if not lin or expect_linear:
+        raise NotImplementedError('edge network must end with a Linear layer (no output nonlinearity)')
+    return lin
+
+
+class _Prepared(object):
+    """nnconv_weights_t: padded / permuted / down-converted snapshot of the edge-MLP parameters."""
+
+    def __init__(self, linears, cin, cout, precision):
+        L = _lib.lib()
+        _lib.check(L.nnconv_init())
+        n = len(linears)
+        dims = [linears[0].in_features] + [l.out_features for l in linears]
+        c_dims = (ctypes.c_int * (n + 1))(*dims)
+        nbytes = ctypes.c_size_t()
+        prec = _lib.PREC[precision]
+        _lib.check(L.nnconv_weights_sizes(n, c_dims, cin, cout, prec, ctypes.byref(nbytes)))
+        dev = linears[0].weight.device
+        self.buf = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        ws = [l.weight.detach().contiguous().float() for l in linears]
+        bs = [l.bias.detach().contiguous().float() for l in linears]
+        wp = (ctypes.c_void_p * n)(*[w.data_ptr() for w in ws])
+        bp = (ctypes.c_void_p * n)(*[b.data_ptr() for b in bs])
+        h = ctypes.c_void_p()
+        _lib.check(L.nnconv_weights_create(n, c_dims, cin, cout, prec, wp, bp, _ptr(self.buf), nbytes.value,
+                                           _stream_ptr(dev), ctypes.byref(h)))
+        self._keep = (ws, bs)
+        self.handle = h
+        self.dims = dims
+        self.precision = precision
+        self.tc = bool(L.nnconv_weights_tc_supported(h))
+        stats['weight_preps'] += 1
+        stats['launches'] += 2 * n + 1
+        self._finalizer = weakref.finalize(self, L.nnconv_weights_destroy, h)
+
+
+class _NNConvFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, edge_index, edge_attr, *params):
+        return module._forward_impl(x, edge_index, edge_attr)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        raise NotImplementedError(
+            'graph_pde_b200.NNConv: the backward pass of the B200 kernel path is not built yet '
+            '(SURVEY 8(a) row a11); run the forward under torch.no_grad()')
+
+
+class NNConv_old(torch.nn.Module):
+    r"""Edge-conditioned convolution  x'_i = Theta x_i + aggr_{j in N(i)} x_j . h_Theta(e_ij)
+    (reference docstring: graph-neural-operator/nn_conv.py:198-232).
+
+    Args are the reference's (nn_conv.py:234-241).  Extra keyword ``precision`` in
+    {'f16' (default), 'bf16', 'fp32'} selects the tensor-core operand type ('fp32' = CUDA-core path for
+    arbitrary shapes); ``flow`` is PyG's MessagePassing kwarg.
+    """
+
+    def __init__(self, in_channels, out_channels, nn, aggr='add', root_weight=True, bias=True, **kwargs):
+        super(NNConv_old, self).__init__()
+        self.precision = kwargs.pop('precision', None)
+        self.flow = kwargs.pop('flow', 'source_to_target')
+        if kwargs:
+            raise TypeError('unexpected keyword arguments %s' % sorted(kwargs))
+        if aggr not in ('add', 'mean', 'max'):
+            raise ValueError("aggr must be 'add', 'mean' or 'max'")
+        if self.flow not in _lib.FLOW:
+            raise ValueError('flow must be source_to_target or target_to_source')
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.nn = nn
+        self.aggr = aggr
+        if root_weight:
+            self.root = Parameter(torch.Tensor(in_channels, out_channels))
+        else:
+            self.register_parameter('root', None)
+        if bias:
+            self.bias = Parameter(torch.Tensor(out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self._prepared = None
+        self._prepared_key = None
+        self._h_cache = collections.OrderedDict()
+        self._h_cache_max = 1
+        self.reset_parameters()
+
+    # -- reference: nn_conv.py:261-265 with torch_geometric.nn.inits.reset / uniform restated ----------
+    def reset_parameters(self):
+        def _reset(m):
+            children = list(m.children()) if hasattr(m, 'children') else []
+            if children:
+                for c in children:
+                    _reset(c)
+            elif hasattr(m, 'reset_parameters'):
+                m.reset_parameters()
+        _reset(self.nn)
+        bound = 1.0 / math.sqrt(self.in_channels)
+        if self.root is not None:
+            self.root.data.uniform_(-bound, bound)
+        if self.bias is not None:
+            self.bias.data.uniform_(-bound, bound)
+
+    # -- reference: nn_conv.py:267-271 ------------------------------------------------------------------
+    def forward(self, x, edge_index, edge_attr):
+        x = x.unsqueeze(-1) if x.dim() == 1 else x
+        pseudo = edge_attr.unsqueeze(-1) if edge_attr.dim() == 1 else edge_attr
+        needs_grad = torch.is_grad_enabled() and (
+            x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_grad:
+            return _NNConvFunction.apply(self, x, edge_index, pseudo, *list(self.parameters()))
+        return self._forward_impl(x, edge_index, pseudo)
+
+    def __repr__(self):
+        return '{}({}, {})'.format(self.__class__.__name__, self.in_channels, self.out_channels)
+
+    # -- host-side sequencing ---------------------------------------------------------------------------
+    def _get_prepared(self, precision):
+        linears = _linear_chain(self.nn)
+        key = (precision,) + tuple((l.weight.data_ptr(), l.weight._version, l.bias.data_ptr(), l.bias._version)
+                                   for l in linears)
+        if self._prepared is None or self._prepared_key != key:
+            self._prepared = _Prepared(linears, self.in_channels, self.out_channels, precision)
+            self._prepared_key = key
+            self._h_cache.clear()
+        return self._prepared
+
+    def edge_features(self, plan, prepared, edge_attr):
+        """x-independent part of message(): cached across the T applications of a shared conv."""
+        key = (plan.key, edge_attr.data_ptr(), tuple(edge_attr.shape), edge_attr._version, id(prepared))
+        hit = self._h_cache.get(key)
+        if hit is not None:
+            return hit[0]
+        L = _lib.lib()
+        h_b, ws_b = ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(L.nnconv_edge_features_sizes(plan.handle, prepared.handle, _EF_WS_BYTES, ctypes.byref(h_b),
+                                                ctypes.byref(ws_b)))
+        dev = edge_attr.device
+        self._h_cache.clear()                       # free the previous sample's features first
+        h = torch.empty(h_b.value, dtype=torch.uint8, device=dev)
+        ws = torch.empty(ws_b.value, dtype=torch.uint8, device=dev)
+        n_l = ctypes.c_int64(0)
+        _lib.check(L.nnconv_edge_features(plan.handle, prepared.handle, _ptr(edge_attr), _ptr(h), _ptr(ws),
+                                          ws_b.value, _stream_ptr(dev), ctypes.byref(n_l)))
+        stats['launches'] += n_l.value
+        stats['edge_feature_passes'] += 1
+        self._h_cache[key] = (h, edge_attr)          # hold edge_attr so its address cannot be recycled
+        return h
+
+    def _forward_impl(self, x, edge_index, pseudo):
+        _require_cuda(x, 'x')
+        _require_cuda(edge_index, 'edge_index')
+        _require_cuda(pseudo, 'edge_attr')
+        if self.aggr == 'max':
+            raise NotImplementedError("aggr='max' is used by no call site of the reference and is not built")
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
+            raise ValueError('edge_index must be an int64 tensor of shape [2, E]')
+        if x.size(1) != self.in_channels:
+            raise ValueError('x has %d channels, expected %d' % (x.size(1), self.in_channels))
+        if pseudo.size(0) != edge_index.size(1):
+            raise ValueError('edge_attr has %d rows for %d edges' % (pseudo.size(0), edge_index.size(1)))
+        precision = self.precision or default_precision()
+        with torch.cuda.device(x.device):
+            x32 = x.detach().contiguous().float()
+            ea32 = pseudo.detach()
+            if ea32.dtype != torch.float32 or not ea32.is_contiguous():
+                ea32 = ea32.contiguous().float()
+            n = x32.size(0)
+            plan = get_plan(edge_index, n, self.flow)
+            prepared = self._get_prepared(precision)
+            h = self.edge_features(plan, prepared, ea32)
+            L = _lib.lib()
+            ws_b = ctypes.c_size_t()
+            _lib.check(L.nnconv_apply_sizes(plan.handle, prepared.handle, _Y_BYTES, ctypes.byref(ws_b)))
+            ws = torch.empty(ws_b.value, dtype=torch.uint8, device=x.device)
+            out = torch.empty(n, self.out_channels, dtype=torch.float32, device=x.device)
+            root = self.root.detach().contiguous().float() if self.root is not None else None
+            bias = self.bias.detach().contiguous().float() if self.bias is not None else None
+            n_l = ctypes.c_int64(0)
+            _lib.check(L.nnconv_apply(plan.handle, prepared.handle, _ptr(h), _ptr(x32), _ptr(root), _ptr(bias),
+                                      _lib.AGGR[self.aggr], _ptr(out), _ptr(ws), ws_b.value, _stream_ptr(x.device),
+                                      ctypes.byref(n_l)))
+            stats['launches'] += n_l.value
+            stats['applies'] += 1
+        return out
+
+
+class NNConv(NNConv_old):
+    """Drop-in for upstream ``torch_geometric.nn.NNConv`` as the MGKN scripts use it
+    (multipole-graph-neural-operator/neurips1_MGKN.py:41,49,57; MGKN_general_darcy2d.py:45,53,61;
+    MGKN_orthogonal_burgers1d.py:37).  NOTE: graph-neural-operator/nn_conv.py:8-96 also defines a class
+    called NNConv (diagonal-kernel variant) which no script instantiates; it is out of scope."""
+    pass
+
+
+ECConv = NNConv

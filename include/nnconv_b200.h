@@ -1,0 +1,126 @@
+/* nnconv_b200.h -- C ABI of libnnconv_b200.so: the NNConv (edge-conditioned convolution) hot path of
+ * neuraloperator/graph-pde, hand-written for NVIDIA B200 (sm_100a).
+ *
+ * What it replaces (paths relative to the reference repo):
+ *   graph-neural-operator/nn_conv.py:267-282   NNConv_old.forward / message / update
+ *   graph-neural-operator/utilities.py:223-227 DenseNet.forward (the edge MLP evaluated inside message)
+ *   torch_geometric MessagePassing.propagate + torch_scatter.scatter_{add,mean} (un-vendored third
+ *   party reached from nn_conv.py:271)
+ * and, through the same entry points, upstream torch_geometric.nn.NNConv as used by
+ *   multipole-graph-neural-operator/neurips1_MGKN.py:41,49,57, MGKN_general_darcy2d.py:45,53,61,
+ *   MGKN_orthogonal_burgers1d.py:37.
+ *
+ * Conventions
+ *   - every function returns 0 on success or an NNCONV_ERR_* code; nnconv_last_error() returns a
+ *     thread-local message.  No C++ exception crosses this boundary.
+ *   - all data pointers are DEVICE pointers on the current CUDA device unless named host_*;
+ *     `stream` is a cudaStream_t passed as void*.
+ *   - the library never allocates device memory: callers query a size, allocate (e.g. through the
+ *     PyTorch caching allocator) and pass the buffer.  Buffers handed to *_create calls must outlive
+ *     the handle.
+ *   - no call synchronises the device except nnconv_plan_create (one-time per graph).
+ *   - re-entrant; no thread-local state apart from the error string.
+ *
+ * Math (identical to the reference up to floating-point association):
+ *   h_e    = DenseNet_without_last_Linear(edge_attr_e)                  (x independent, "edge features")
+ *   K_e    = (W_L h_e + b_L).view(in, out)                              nn_conv.py:274
+ *   m_e    = x[src_e] @ K_e                                             nn_conv.py:275
+ *   out_n  = aggr_{e: dst_e = n} m_e  + x_n @ root + bias               nn_conv.py:277-282
+ * with flow = source_to_target: src = edge_index[0], dst = edge_index[1]; mean of an empty
+ * neighbourhood is 0.
+ */
+#ifndef NNCONV_B200_H_
+#define NNCONV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNCONV_B200_ABI_VERSION 1
+
+/* status codes */
+#define NNCONV_OK 0
+#define NNCONV_ERR_ARG 1
+#define NNCONV_ERR_CUDA 2
+#define NNCONV_ERR_WORKSPACE 3
+#define NNCONV_ERR_UNSUPPORTED 4
+
+/* precision of the tensor-core operands (accumulation is always fp32; x@root+bias and the first
+ * MLP layer are always fp32 CUDA-core math) */
+#define NNCONV_PREC_FP32 0 /* CUDA-core fp32 everywhere, any shape */
+#define NNCONV_PREC_F16 1  /* tcgen05 kind::f16, fp16 operands (10-bit mantissa, TF32-grade) */
+#define NNCONV_PREC_BF16 2 /* tcgen05 kind::f16, bf16 operands */
+
+#define NNCONV_AGGR_ADD 0
+#define NNCONV_AGGR_MEAN 1
+
+#define NNCONV_FLOW_SOURCE_TO_TARGET 0
+#define NNCONV_FLOW_TARGET_TO_SOURCE 1
+
+typedef struct nnconv_plan nnconv_plan_t;       /* per edge_index: source grouping, tiles, degrees */
+typedef struct nnconv_weights nnconv_weights_t; /* per parameter version: padded/permuted MLP weights */
+
+const char* nnconv_last_error(void);
+int nnconv_abi_version(void);
+/* checks the device (sm_100 class) and resolves the TMA descriptor encoder; idempotent */
+int nnconv_init(void);
+
+/* ---- plan: replaces the implicit structure PyG derives from edge_index inside propagate() -------- */
+int nnconv_plan_sizes(int64_t E, int64_t N, size_t* ws_bytes, size_t* tmp_bytes);
+/* row0 / row1: the two int64 rows of edge_index [2, E] (nn_conv.py:267 argument); passing the rows
+ * separately lets a column slice edge_index[:, a:b] (neurips1_MGKN.py:75) be used without a copy.
+ * ws stays owned by the plan, tmp may be freed on return.  Synchronises `stream` (returns tile counts
+ * to the host). */
+int nnconv_plan_create(const int64_t* row0, const int64_t* row1, int64_t E, int64_t N, int flow, void* ws, size_t ws_bytes,
+                       void* tmp, size_t tmp_bytes, void* stream, nnconv_plan_t** out);
+void nnconv_plan_destroy(nnconv_plan_t* plan);
+/* info[0..6] = E, N, #sources with out-edges, #tiles, max out-degree, already-grouped flag, flow */
+int nnconv_plan_info(const nnconv_plan_t* plan, int64_t* info, int n_info);
+
+/* ---- weights: snapshot of the edge MLP ("nn" argument of NNConv_old.__init__, nn_conv.py:234-246) -- */
+/* dims[0..n_layers] = k_in, k_1, ..., in_channels*out_channels;  W[l]: [dims[l+1], dims[l]] fp32
+ * (torch.nn.Linear layout, utilities.py:212-213), b[l]: [dims[l+1]].  W and b are HOST arrays of device
+ * pointers. */
+int nnconv_weights_sizes(int n_layers, const int* dims, int in_channels, int out_channels, int precision,
+                         size_t* bytes);
+int nnconv_weights_create(int n_layers, const int* dims, int in_channels, int out_channels, int precision,
+                          const float* const* W, const float* const* b, void* buf, size_t buf_bytes, void* stream,
+                          nnconv_weights_t** out);
+void nnconv_weights_destroy(nnconv_weights_t* w);
+int nnconv_weights_tc_supported(const nnconv_weights_t* w);
+
+/* ---- hoisted, x-independent part of message(): h_e for every edge (utilities.py:223-227 minus the
+ * last Linear).  Valid as long as edge_attr and the weights are unchanged, i.e. for all T applications
+ * of the shared conv inside KernelNN.forward (UAI1_full_resolution.py:29-30). ------------------------ */
+int nnconv_edge_features_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t want_ws_bytes,
+                               size_t* h_bytes, size_t* ws_bytes);
+int nnconv_edge_features(const nnconv_plan_t* plan, const nnconv_weights_t* w, const float* edge_attr /*[E,k_in]*/,
+                         void* h, void* ws, size_t ws_bytes, void* stream, int64_t* launches /*nullable*/);
+
+/* ---- one NNConv application: gather + last Linear + per-edge contraction + scatter + root + bias --- */
+int nnconv_apply_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t want_y_bytes, size_t* ws_bytes);
+/* x [N,in] fp32, root [in,out] or NULL, bias [out] or NULL, out [N,out] fp32 (fully overwritten). */
+int nnconv_apply(const nnconv_plan_t* plan, const nnconv_weights_t* w, const void* h, const float* x,
+                 const float* root, const float* bias, int aggr, float* out, void* ws, size_t ws_bytes, void* stream,
+                 int64_t* launches /*nullable*/);
+
+/* ---- measurement hook (bench.py): while enabled, every kernel launch is bracketed by CUDA events on its
+ * stream; profile_end synchronises the device and returns summed milliseconds / launch counts per kernel
+ * class: 0 first MLP layer, 1 hidden-layer GEMM, 2 per-node prologue, 3 per-source Y GEMM,
+ * 4 contraction+scatter.  Not thread safe; not for production use. */
+#define NNCONV_PROFILE_KINDS 5
+int nnconv_profile_begin(void);
+int nnconv_profile_end(double* ms_by_kind, int64_t* launches_by_kind, int n_kinds);
+
+/* ---- unit-test hook for the tcgen05 GEMM used by the hidden layers and the per-source matrices:
+ * C[M,N] (16-bit) = act(A[M,K] * B[N,K]^T + bias); K, N multiples of 64; bias nullable. ------------- */
+int nnconv_gemm_16b(int precision, const void* A, int64_t M, int K, const void* B, int N, const float* bias,
+                    int relu, void* C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNCONV_B200_H_ */

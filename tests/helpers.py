@@ -1,0 +1,71 @@
+"""Shared helpers for the parity tests (CPU side: golden loaders; GPU side: module builders)."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+# stated tolerances: max|out - ref| / max|ref| per tensor-core operand precision (DESIGN.md "Precision")
+TOL = {'fp32': 2e-5, 'f16': 2e-3, 'bf16': 2e-2}
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def ei64(a):
+    return torch.from_numpy(np.asarray(a).astype(np.int64))
+
+
+def rel_err(out, ref):
+    out = out.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    return float((out - ref).abs().max() / ref.abs().max().clamp(min=1e-30))
+
+
+def cfg1_weights(g):
+    """Re-draw the seeded KernelNN(w=32, kw=1024) parameters of golden G2 (same stream as the reference)."""
+    w, kw = int(g['width']), int(g['ker_width'])
+    torch.manual_seed(0)
+    fc1 = torch.nn.Linear(6, w)
+    lins = [torch.nn.Linear(a, b) for a, b in zip([6, kw, kw], [kw, kw, w * w])]
+    for lin in lins:
+        lin.reset_parameters()
+    root = torch.empty(w, w).uniform_(-1 / np.sqrt(w), 1 / np.sqrt(w))
+    bias = torch.empty(w).uniform_(-1 / np.sqrt(w), 1 / np.sqrt(w))
+    return fc1, [l.weight.detach() for l in lins], [l.bias.detach() for l in lins], root, bias
+
+
+class DenseNetLike(torch.nn.Module):
+    """Same module tree / state-dict keys as the reference's DenseNet (utilities.py:201-227):
+    self.layers = ModuleList([Linear, ReLU, Linear, ..., Linear])."""
+
+    def __init__(self, layers):
+        super().__init__()
+        self.layers = torch.nn.ModuleList()
+        for j in range(len(layers) - 1):
+            self.layers.append(torch.nn.Linear(layers[j], layers[j + 1]))
+            if j != len(layers) - 2:
+                self.layers.append(torch.nn.ReLU())
+
+    def forward(self, x):
+        for l in self.layers:
+            x = l(x)
+        return x
+
+
+def make_conv(cls, ws, bs, root, bias, aggr, cin, cout, precision, device):
+    dims = [ws[0].shape[1]] + [w.shape[0] for w in ws]
+    mlp = DenseNetLike(dims)
+    conv = cls(cin, cout, mlp, aggr=aggr, root_weight=root is not None, bias=bias is not None, precision=precision)
+    with torch.no_grad():
+        lin = [m for m in mlp.layers if isinstance(m, torch.nn.Linear)]
+        for l, w, b in zip(lin, ws, bs):
+            l.weight.copy_(torch.as_tensor(w))
+            l.bias.copy_(torch.as_tensor(b))
+        if root is not None:
+            conv.root.copy_(torch.as_tensor(root))
+        if bias is not None:
+            conv.bias.copy_(torch.as_tensor(bias))
+    return conv.to(device)

@@ -1,0 +1,167 @@
+"""GPU parity: the CUDA path (through the C ABI of libnnconv_b200.so) vs golden vectors produced by the
+reference's own files and vs the CPU oracle on seeded inputs.  Run on the B200 box: pytest -m gpu."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nnconv_oracle as O
+from tests.helpers import GOLDEN, TOL, DenseNetLike, cfg1_weights, ei64, make_conv, rel_err, t
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device('cuda:0')
+
+
+def _conv_cls():
+    from graph_pde_b200.nn_conv import NNConv_old
+    return NNConv_old
+
+
+def test_library_loaded_and_device_ok(dev):
+    from graph_pde_b200 import _lib
+    L = _lib.lib()
+    assert L.nnconv_abi_version() == 1
+    _lib.check(L.nnconv_init())
+
+
+def test_g1_tiny_multigraph_all_flags_fp32(dev):
+    """in=5/out=7 is not a tensor-core shape: exercises the CUDA-core fp32 path, duplicates, isolated nodes."""
+    g = np.load(os.path.join(GOLDEN, 'g1_tiny_multigraph.npz'))
+    ei, ea, x = ei64(g['edge_index']).to(dev), t(g['edge_attr']).to(dev), t(g['x']).to(dev)
+    for aggr in ('mean', 'add'):
+        for rw in (1, 0):
+            for bs in (1, 0):
+                tag = '%s_r%d_b%d' % (aggr, rw, bs)
+                ws = [g[tag + '/nn.layers.0.weight'], g[tag + '/nn.layers.2.weight']]
+                bsl = [g[tag + '/nn.layers.0.bias'], g[tag + '/nn.layers.2.bias']]
+                conv = make_conv(_conv_cls(), ws, bsl, g[tag + '/root'] if rw else None,
+                                 g[tag + '/bias'] if bs else None, aggr, 5, 7, 'fp32', dev)
+                with torch.no_grad():
+                    out = conv(x, ei, ea)
+                assert rel_err(out, t(g[tag + '/out'])) < TOL['fp32'], tag
+    ws = [g['oned/nn.layers.0.weight'], g['oned/nn.layers.2.weight']]
+    bsl = [g['oned/nn.layers.0.bias'], g['oned/nn.layers.2.bias']]
+    conv = make_conv(_conv_cls(), ws, bsl, g['oned/root'], g['oned/bias'], 'mean', 1, 4, 'fp32', dev)
+    with torch.no_grad():
+        out = conv(t(g['oned/x']).to(dev), ei, t(g['oned/edge_attr']).to(dev))     # 1-D x and edge_attr
+    assert rel_err(out, t(g['oned/out'])) < TOL['fp32']
+
+
+@pytest.mark.parametrize('precision', ['f16', 'bf16', 'fp32'])
+def test_g2_cfg1_conv_stack(dev, precision):
+    """BASELINE config 1: 16x16, r=0.25, w=32, ker_width=1024, T=4 -- every iteration vs the reference."""
+    g = np.load(os.path.join(GOLDEN, 'g2_cfg1_ball16.npz'))
+    fc1, ws, bs, root, bias = cfg1_weights(g)
+    conv = make_conv(_conv_cls(), ws, bs, root, bias, 'mean', 32, 32, precision, dev)
+    ei, ea = ei64(g['edge_index']).to(dev), t(g['edge_attr']).to(dev)
+    x = t(g['x0']).to(dev)
+    with torch.no_grad():
+        for k in range(int(g['depth'])):
+            x = torch.relu(conv(x, ei, ea))
+            assert rel_err(x, t(g['x_after'][k])) < TOL[precision], (precision, k)
+
+
+@pytest.mark.parametrize('precision', ['f16', 'bf16', 'fp32'])
+def test_g3_checkpoint_weights(dev, precision):
+    """Trained weights shipped by the reference (graph-neural-operator/model/grain_new_r64_s64testm100)."""
+    g = np.load(os.path.join(GOLDEN, 'g3_checkpoint_grain_new.npz'))
+    st = {k[2:]: g[k] for k in g.files if k.startswith('w/')}
+    ws = [st['conv1.nn.layers.%d.weight' % i] for i in (0, 2, 4)]
+    bs = [st['conv1.nn.layers.%d.bias' % i] for i in (0, 2, 4)]
+    conv = make_conv(_conv_cls(), ws, bs, st['conv1.root'], st['conv1.bias'], 'mean', 64, 64, precision, dev)
+    ei, ea = ei64(g['edge_index']).to(dev), t(g['edge_attr']).to(dev)
+    x = t(g['x0']).to(dev)
+    with torch.no_grad():
+        for k in range(6):
+            x = torch.relu(conv(x, ei, ea))
+            assert rel_err(x, t(g['x_after'][k])) < TOL[precision], (precision, k)
+
+
+@pytest.mark.parametrize('precision', ['f16', 'fp32'])
+@pytest.mark.parametrize('layers', [[6, 64, 4096], [4, 128, 64, 4096], [6, 32, 64, 48, 128, 4096], [3, 4096]])
+def test_random_multigraph_unsorted_sources(dev, precision, layers):
+    """Edges NOT grouped by source (exercises the radix-sort plan), hub node with > 128 out-edges, isolated
+    nodes, duplicate edges, nodes with no in-edges (mean of the empty set = 0), 1..5 layer edge MLPs."""
+    gen = torch.Generator().manual_seed(5)
+    N, E, w = 300, 5000, 64
+    src = torch.randint(0, N - 20, (E,), generator=gen)
+    dst = torch.randint(10, N, (E,), generator=gen)
+    src[:700] = 7                                   # hub: several tiles for one source
+    src[1000:1010] = src[1000]
+    dst[1000:1010] = dst[1000]
+    ei = torch.stack([src, dst])
+    ea = torch.randn(E, layers[0], generator=gen)
+    x = torch.randn(N, w, generator=gen)
+    torch.manual_seed(11)
+    mlp = DenseNetLike(layers)
+    lin = [m for m in mlp.layers if isinstance(m, torch.nn.Linear)]
+    ws, bs = [l.weight.detach() for l in lin], [l.bias.detach() for l in lin]
+    for aggr in ('mean', 'add'):
+        conv = make_conv(_conv_cls(), ws, bs, torch.randn(w, w) * 0.1, torch.randn(w) * 0.1, aggr, w, w,
+                         precision, dev)
+        ref = O.nnconv_forward(x, ei, ea, ws, bs, conv.root.detach().cpu(), conv.bias.detach().cpu(), aggr)
+        with torch.no_grad():
+            out = conv(x.to(dev), ei.to(dev), ea.to(dev))
+        assert rel_err(out, ref) < TOL[precision], (aggr, layers)
+
+
+def test_edge_subset_call_and_zero_edges(dev):
+    """MGKN style: N >> touched nodes, column-sliced edge_index view, no root / no bias; and E = 0."""
+    gen = torch.Generator().manual_seed(9)
+    N, E, w = 500, 3000, 64
+    ei_all = torch.stack([torch.randint(0, 60, (E,), generator=gen), torch.randint(100, 180, (E,), generator=gen)])
+    ei_all = ei_all[:, torch.argsort(ei_all[0], stable=True)]
+    ea_all = torch.randn(E, 6, generator=gen)
+    x = torch.randn(N, w, generator=gen)
+    torch.manual_seed(3)
+    mlp = DenseNetLike([6, 64, w * w])
+    lin = [m for m in mlp.layers if isinstance(m, torch.nn.Linear)]
+    ws, bs = [l.weight.detach() for l in lin], [l.bias.detach() for l in lin]
+    conv = make_conv(_conv_cls(), ws, bs, None, None, 'mean', w, w, 'f16', dev)
+    ei_d, ea_d, x_d = ei_all.to(dev), ea_all.to(dev), x.to(dev)
+    a, b = 500, 2100
+    with torch.no_grad():
+        out = conv(x_d, ei_d[:, a:b], ea_d[a:b, :])          # non-contiguous view, as neurips1_MGKN.py:75
+        out0 = conv(x_d, ei_d[:, 0:0], ea_d[0:0, :])
+    ref = O.nnconv_forward(x, ei_all[:, a:b], ea_all[a:b], ws, bs, None, None, 'mean')
+    assert rel_err(out, ref) < TOL['f16']
+    assert float(out0.abs().max()) == 0.0
+
+
+def test_properties_at_config2_size(dev):
+    """BASELINE config 2 size (85x85, r=0.10, w=64, ker_width=1024): oracle on a sample of target nodes plus
+    size-independent properties (linearity in x, mean == add / in-degree, determinism of the cached features)."""
+    s, r, w, kw = 85, 0.10, 64, 1024
+    ei = torch.from_numpy(O.ball_connectivity(s, r))
+    assert ei.size(1) == 1466497                       # exact, no lattice ties
+    rs = np.random.RandomState(0)
+    theta = rs.randn(s * s)
+    ea = torch.from_numpy(O.ball_edge_attr(O.square_grid(s), ei.numpy(), theta))
+    torch.manual_seed(0)
+    x = torch.randn(s * s, w)
+    ws, bs, root, bias = O.reference_init(w, w, [6, kw, kw, w * w], seed=0)
+    conv = make_conv(_conv_cls(), ws, bs, root, bias, 'mean', w, w, 'f16', dev)
+    conv_add = make_conv(_conv_cls(), ws, bs, None, None, 'add', w, w, 'f16', dev)
+    conv_mean = make_conv(_conv_cls(), ws, bs, None, None, 'mean', w, w, 'f16', dev)
+    ei_d, ea_d, x_d = ei.to(dev), ea.to(dev), x.to(dev)
+    with torch.no_grad():
+        out = conv(x_d, ei_d, ea_d)
+        out2 = conv(2.5 * x_d, ei_d, ea_d)
+        o_add = conv_add(x_d, ei_d, ea_d)
+        o_mean = conv_mean(x_d, ei_d, ea_d)
+    # oracle on the edges that end in 24 sampled target nodes
+    nodes = torch.from_numpy(rs.choice(s * s, 24, replace=False))
+    mask = torch.isin(ei[1], nodes)
+    ref = O.nnconv_forward(x, ei[:, mask], ea[mask], ws, bs, root, bias, 'mean', edge_chunk=2048)
+    assert rel_err(out.cpu()[nodes], ref[nodes]) < TOL['f16']
+    # linearity in x (bias is the only affine part)
+    lin_err = rel_err(out2 - bias.to(dev), 2.5 * (out - bias.to(dev)))
+    assert lin_err < 2e-3
+    deg = torch.zeros(s * s).index_add_(0, ei[1], torch.ones(ei.size(1))).clamp(min=1).to(dev)
+    assert rel_err(o_mean, o_add / deg[:, None]) < 1e-5
