@@ -3,6 +3,7 @@
 // nnconv_plan_create (one-time per graph, returns counts to the host).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -45,7 +46,7 @@ static size_t esize_of(int prec) { return prec == PREC_FP32 ? 4 : 2; }
 // prepared weights
 // ------------------------------------------------------------------------------------------------
 struct WeightsLayout {
-  size_t off_W1, off_b1, off_Wh[kMaxLayers], off_bh[kMaxLayers], off_W3p, off_B3, bytes;
+  size_t off_W1, off_b1, off_W1aug, off_Wh[kMaxLayers], off_bh[kMaxLayers], off_W3p, off_B3, bytes;
 };
 
 static int fill_dims(Weights* W, int n_layers, const int* dims, int cin, int cout, int prec) {
@@ -78,6 +79,7 @@ static WeightsLayout layout_weights(const Weights* W) {
   if (nl >= 2) {
     L.off_W1 = c.off; c.take<float>(static_cast<size_t>(W->kp[1]) * W->dims[0]);
     L.off_b1 = c.off; c.take<float>(W->kp[1]);
+    L.off_W1aug = c.off; c.take<char>(static_cast<size_t>(W->kp[1]) * 64 * 2);
   }
   for (int l = 2; l <= nl - 1; ++l) {
     L.off_Wh[l] = c.off; c.take<char>(static_cast<size_t>(W->kp[l]) * W->kp[l - 1] * W->esize);
@@ -113,6 +115,12 @@ int weights_prepare(Weights* W, int n_layers, const int* dims, int cin, int cout
     if (s) return s;
     W->W1 = W1;
     W->b1 = b1;
+    if (prec != PREC_FP32 && 3 * dims[0] + 2 <= 64) {   // split-precision first layer on the tensor cores
+      void* aug = base + L.off_W1aug;
+      s = launch_w1aug(prec, W1, b1, dims[1], W->kp[1], dims[0], aug, st);
+      if (s) return s;
+      W->W1aug = aug;
+    }
   }
   for (int l = 2; l <= nl - 1; ++l) {
     void* Wh = base + L.off_Wh[l];
@@ -144,15 +152,23 @@ static int max_hidden_kp(const Weights* W) {
   return m;
 }
 
+static size_t ef_row_bytes(const Weights* W) {
+  // per edge row of workspace: A1 (64 x 16-bit, tensor-core first layer) + ping/pong hidden activations
+  size_t row = 0;
+  if (W->W1aug) row += 128;
+  if (W->n_layers > 2) row += 2 * static_cast<size_t>(max_hidden_kp(W)) * W->esize;
+  return row;
+}
+
 size_t edge_features_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes) {
-  if (W->n_layers <= 2) return 1024;   // h_last is written directly by the first-layer kernel
-  const size_t row = 2 * static_cast<size_t>(max_hidden_kp(W)) * W->esize;   // ping + pong
+  const size_t row = ef_row_bytes(W);
+  if (row == 0) return 1024;   // h_last is written directly by the CUDA-core first-layer kernel
   size_t rows_all = static_cast<size_t>(round_up64(P->E > 0 ? P->E : 1, 128));
   size_t rows = want_bytes / row;
   rows = rows / 128 * 128;
   if (rows < 128) rows = 128;
   if (rows > rows_all) rows = rows_all;
-  return rows * row + 2048;
+  return rows * row + 4096;
 }
 
 int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void* h, void* ws, size_t ws_bytes,
@@ -164,28 +180,44 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
   NNC_REQUIRE(tc || W->prec == PREC_FP32, NNCONV_ERR_UNSUPPORTED,
               "shape not supported by the tensor-core path (out=%d, K=%d); use precision fp32", W->cout, W->K);
   int s;
+  // 16-bit path: h is chunk-major [Kp/64][E_pad][64] (what the contraction kernel streams); fp32: row-major
+  const int64_t hpad = W->prec == PREC_FP32 ? 0 : round_up64(E, 128);
   if (nl == 1) {   // single Linear: h_last = edge_attr (padded)
     ProfScope ps(PK_LAYER1, st);
-    s = launch_edge_layer1(W->prec, edge_attr, P->perm, 0, E, W->dims[0], nullptr, nullptr, W->Kp, 1, h, st);
+    s = launch_edge_layer1(W->prec, edge_attr, P->perm, 0, E, W->dims[0], nullptr, nullptr, W->Kp, 1, h, st, hpad, 0);
     if (launches) ++*launches;
     return s;
   }
-  if (nl == 2) {   // h_last = relu(Linear_1)
+  const size_t rowb = ef_row_bytes(W);
+  if (rowb == 0) {   // CUDA-core first layer straight into h (fp32 path, 2-layer MLP)
     ProfScope ps(PK_LAYER1, st);
-    s = launch_edge_layer1(W->prec, edge_attr, P->perm, 0, E, W->dims[0], W->W1, W->b1, W->kp[1], 0, h, st);
+    s = launch_edge_layer1(W->prec, edge_attr, P->perm, 0, E, W->dims[0], W->W1, W->b1, W->kp[1], 0, h, st, hpad, 0);
     if (launches) ++*launches;
     return s;
   }
-  const size_t row = static_cast<size_t>(max_hidden_kp(W)) * W->esize;
-  NNC_REQUIRE(ws != nullptr && ws_bytes >= 2 * 128 * row + 2048, NNCONV_ERR_WORKSPACE, "edge_features: workspace too small");
-  int64_t rows = static_cast<int64_t>((ws_bytes - 2048) / (2 * row)) / 128 * 128;
-  char* bufA = static_cast<char*>(ws);
-  char* bufB = bufA + round_up64(static_cast<int64_t>(rows * row), 1024);
+  NNC_REQUIRE(ws != nullptr && ws_bytes >= 128 * rowb + 4096, NNCONV_ERR_WORKSPACE, "edge_features: workspace too small");
+  const int64_t rows = static_cast<int64_t>((ws_bytes - 4096) / rowb) / 128 * 128;
+  const size_t hid = static_cast<size_t>(max_hidden_kp(W)) * W->esize;
+  char* a1 = static_cast<char*>(ws);
+  char* bufA = a1 + (W->W1aug ? round_up64(rows * 128, 1024) : 0);
+  char* bufB = bufA + round_up64(static_cast<int64_t>(rows * hid), 1024);
   for (int64_t e0 = 0; e0 < E; e0 += rows) {
     const int64_t n = (E - e0) < rows ? (E - e0) : rows;
+    void* h_rows = hpad > 0 ? h : static_cast<void*>(static_cast<char*>(h) + static_cast<size_t>(e0) * W->Kp * W->esize);
+    const int64_t h_pad_l1 = nl == 2 ? hpad : 0;     // first layer writes h directly only for 2-layer MLPs
+    void* dst1 = nl == 2 ? h_rows : static_cast<void*>(bufA);
     {
       ProfScope ps(PK_LAYER1, st);
-      s = launch_edge_layer1(W->prec, edge_attr, P->perm, e0, n, W->dims[0], W->W1, W->b1, W->kp[1], 0, bufA, st);
+      if (W->W1aug) {
+        s = launch_build_a1(W->prec, edge_attr, P->perm, e0, n, W->dims[0], a1, st);
+        if (s) return s;
+        s = launch_gemm_tc(W->prec, a1, n, 0, static_cast<int>(n), 64, W->W1aug, W->kp[1], nullptr, 1, dst1,
+                           W->kp[1], st, nullptr, h_pad_l1, e0);
+        if (launches) ++*launches;
+      } else {
+        s = launch_edge_layer1(W->prec, edge_attr, P->perm, e0, n, W->dims[0], W->W1, W->b1, W->kp[1], 0, dst1, st,
+                               h_pad_l1, e0);
+      }
     }
     if (s) return s;
     if (launches) ++*launches;
@@ -193,8 +225,7 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
     char* nxt = bufB;
     for (int l = 2; l <= nl - 1; ++l) {
       const bool last = l == nl - 1;
-      void* dst = last ? static_cast<void*>(static_cast<char*>(h) + static_cast<size_t>(e0) * W->Kp * W->esize)
-                       : static_cast<void*>(nxt);
+      void* dst = last ? h_rows : static_cast<void*>(nxt);
       ProfScope ps(PK_HIDDEN_GEMM, st);
       if (W->prec == PREC_FP32) {
         s = launch_sgemm_store(reinterpret_cast<const float*>(cur), W->kp[l - 1],
@@ -202,7 +233,7 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
                                W->kp[l], static_cast<int>(n), W->kp[l], W->kp[l - 1], W->bh[l], st);
       } else {
         s = launch_gemm_tc(W->prec, cur, n, 0, static_cast<int>(n), W->kp[l - 1], W->Wh[l], W->kp[l], W->bh[l], 1,
-                           dst, W->kp[l], st);
+                           dst, W->kp[l], st, nullptr, last ? hpad : 0, e0);
       }
       if (s) return s;
       if (launches) ++*launches;
@@ -216,8 +247,9 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
 // one conv application
 // ------------------------------------------------------------------------------------------------
 struct ApplyLayout {
-  size_t off_Xc, off_cvec, off_Y, fixed_bytes, per_node;
+  size_t off_Xc, off_cvec, off_flags, off_Y, fixed_bytes, per_node;
 };
+constexpr int kMaxPipeBatches = 1 << 14;   // flags: cntY, cntC, okY, okC per batch
 
 static ApplyLayout layout_apply(const Plan* P, const Weights* W) {
   Carver c(nullptr, ~size_t(0));
@@ -225,6 +257,7 @@ static ApplyLayout layout_apply(const Plan* P, const Weights* W) {
   const size_t S = P->n_src > 0 ? P->n_src : 1;
   L.off_Xc = c.off; c.take<char>((S + 128) * W->cin_p * W->esize);
   L.off_cvec = c.off; c.take<float>(S * W->cout);
+  L.off_flags = c.off; c.take<int>(4 * kMaxPipeBatches);
   L.off_Y = c.off;
   L.fixed_bytes = c.off;
   L.per_node = static_cast<size_t>(W->cout) * W->Kp * W->esize;
@@ -259,43 +292,105 @@ int apply(const Plan* P, const Weights* W, const void* h, const float* x, const 
   void* Xc = base + L.off_Xc;
   float* cvec = reinterpret_cast<float*>(base + L.off_cvec);
   void* Y = base + L.off_Y;
-  int64_t nb_max = static_cast<int64_t>((ws_bytes - L.fixed_bytes) / L.per_node);
-  if (nb_max > P->n_src) nb_max = P->n_src;
+  int64_t nodes_cap = static_cast<int64_t>((ws_bytes - L.fixed_bytes) / L.per_node);
   {
     ProfScope ps(PK_NODE_PREP, st);
     s = launch_src_prep(W->prec, x, P->src_nodes, P->n_src, W->cin, W->cin_p, W->cout, W->B3, Xc, cvec, st);
   }
   if (s) return s;
   if (launches) ++*launches;
-  // tile_ptr lives on the device; tile ranges per batch are derived on the host from a small mirror
-  // kept in the plan handle (see nnconv_plan_create).
+  // tile_ptr lives on the device; tile ranges per batch come from the host mirror kept in the plan handle
   const int* h_tile_ptr = P->h_tile_ptr;
   const int NY = W->cout * W->Kp;
-  for (int64_t c0 = 0; c0 < P->n_src; c0 += nb_max) {
-    const int nb = static_cast<int>((P->n_src - c0) < nb_max ? (P->n_src - c0) : nb_max);
-    const int tb = h_tile_ptr[c0], te = h_tile_ptr[c0 + nb];
-    {
-      ProfScope ps(PK_Y_GEMM, st);
-      if (W->prec == PREC_FP32)
+
+  if (W->prec == PREC_FP32) {   // CUDA-core path: plain stream order, one Y buffer
+    int64_t nb_max = nodes_cap > P->n_src ? P->n_src : nodes_cap;
+    for (int64_t c0 = 0; c0 < P->n_src; c0 += nb_max) {
+      const int nb = static_cast<int>((P->n_src - c0) < nb_max ? (P->n_src - c0) : nb_max);
+      const int tb = h_tile_ptr[c0], te = h_tile_ptr[c0 + nb];
+      {
+        ProfScope ps(PK_Y_GEMM, st);
         s = launch_sgemm_store(reinterpret_cast<const float*>(Xc) + c0 * W->cin_p, W->cin_p,
                                reinterpret_cast<const float*>(W->W3p), W->cin_p, static_cast<float*>(Y), NY, nb, NY,
                                W->cin_p, nullptr, st);
-      else
-        s = launch_gemm_tc(W->prec, Xc, P->n_src, c0, nb, W->cin_p, W->W3p, NY, nullptr, 0, Y, NY, st);
-    }
-    if (s) return s;
-    {
-      ProfScope ps(PK_CONV, st);
-      if (W->prec == PREC_FP32)
+      }
+      if (s) return s;
+      {
+        ProfScope ps(PK_CONV, st);
         s = launch_sgemm_scatter(P, static_cast<const float*>(h), W->Kp, static_cast<const float*>(Y), W->cout, tb,
                                  te, static_cast<int>(c0), cvec, aggr_mean, out, st);
-      else
-        s = launch_conv_tc(W->prec, P, h, W->Kp, Y, nb, W->cout, tb, te, static_cast<int>(c0), cvec, aggr_mean, out,
-                           st);
+      }
+      if (s) return s;
+      if (launches) *launches += 2;
     }
-    if (s) return s;
-    if (launches) *launches += 2;
+    return NNCONV_OK;
   }
+
+  // Tensor-core path.  Batches of sources sized so that two Y buffers stay L2 resident; kernel order
+  //   Y(0), Y(1), C(0), Y(2), C(1), ..., C(B-1)            (three Y buffers, b mod 3)
+  // launched with programmatic stream serialization, so CTAs of the next kernel start on SMs as CTAs of
+  // the running kernel retire; the true dependencies  C(b) <- Y(b)  and  Y(b) <- C(b-3) (buffer reuse)
+  // are completion flags in global memory.  Profiling mode (events between kernels) falls back to plain
+  // stream order so that per-kernel times are meaningful.
+  static const bool no_pipe_env = getenv("NNCONV_NO_PIPE") != nullptr;   // measurement / debugging knob
+  const bool pipe = !prof_enabled() && !no_pipe_env && nodes_cap >= 3;
+  int64_t nb_max = pipe ? nodes_cap / 3 : nodes_cap;
+  if (nb_max > P->n_src) nb_max = P->n_src;
+  int64_t n_batches = ceil_div64(P->n_src, nb_max);
+  if (n_batches > kMaxPipeBatches) {   // keep the flag table bounded: grow batches past the L2 target
+    NNC_REQUIRE(false, NNCONV_ERR_WORKSPACE, "apply: workspace too small for %lld source batches", (long long)n_batches);
+  }
+  int* flags = reinterpret_cast<int*>(base + L.off_flags);
+  int* cntY = flags;
+  int* cntC = flags + kMaxPipeBatches;
+  int* okY = flags + 2 * kMaxPipeBatches;
+  int* okC = flags + 3 * kMaxPipeBatches;
+  if (pipe) NNC_CHECK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 4 * kMaxPipeBatches, st));
+  // three Y buffers: Y(b+2) is launched right after C(b) and reuses the buffer C(b-1) read, which has
+  // retired by then -- with two buffers Y(b+2) would have to wait for the kernel it directly follows
+  char* Ybuf[3] = {static_cast<char*>(Y), static_cast<char*>(Y) + (pipe ? nb_max * L.per_node : 0),
+                   static_cast<char*>(Y) + (pipe ? 2 * nb_max * L.per_node : 0)};
+
+  auto launch_y = [&](int64_t b) -> int {
+    const int64_t c0 = b * nb_max;
+    const int nb = static_cast<int>((P->n_src - c0) < nb_max ? (P->n_src - c0) : nb_max);
+    PipeFlags pf{};
+    pf.pdl = pipe && b > 0;
+    pf.wait_ok = (pipe && b >= 3) ? okC + (b - 3) : nullptr;
+    pf.done_cnt = pipe ? cntY + b : nullptr;
+    pf.done_ok = pipe ? okY + b : nullptr;
+    ProfScope ps(PK_Y_GEMM, st);
+    return launch_gemm_tc(W->prec, Xc, P->n_src, c0, nb, W->cin_p, W->W3p, NY, nullptr, 0, Ybuf[b % 3], NY, st,
+                          pipe ? &pf : nullptr);
+  };
+  auto launch_c = [&](int64_t b) -> int {
+    const int64_t c0 = b * nb_max;
+    const int nb = static_cast<int>((P->n_src - c0) < nb_max ? (P->n_src - c0) : nb_max);
+    const int tb = h_tile_ptr[c0], te = h_tile_ptr[c0 + nb];
+    PipeFlags pf{};
+    pf.pdl = pipe;
+    pf.wait_ok = pipe ? okY + b : nullptr;
+    pf.done_cnt = pipe ? cntC + b : nullptr;
+    pf.done_ok = pipe ? okC + b : nullptr;
+    if (pipe && b == n_batches - 1) {   // last kernel of the chain: join every earlier conv kernel
+      pf.join_ok = okC;
+      pf.join_n = static_cast<int>(n_batches - 1);
+    }
+    ProfScope ps(PK_CONV, st);
+    return launch_conv_tc(W->prec, P, h, W->Kp, Ybuf[b % 3], nb, W->cout, tb, te, static_cast<int>(c0), cvec,
+                          aggr_mean, out, st, pipe ? &pf : nullptr);
+  };
+  s = launch_y(0);
+  if (s) return s;
+  for (int64_t b = 0; b < n_batches; ++b) {
+    if (b + 1 < n_batches) {
+      s = launch_y(b + 1);
+      if (s) return s;
+    }
+    s = launch_c(b);
+    if (s) return s;
+  }
+  if (launches) *launches += 2 * n_batches;
   return NNCONV_OK;
 }
 

@@ -17,6 +17,8 @@
 //   * 4 epilogue warps read TMEM (thread = edge row), add c_src, scale by 1/deg(dst) and scatter with
 //     red.global.add.v4.f32 (16 B per request) into out[dst] (fp32, L2 resident).
 // Persistent: grid = #SMs, each CTA owns a contiguous range of tiles (so groups are rarely split).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "tc05.cuh"
 #include "tmap.h"
@@ -45,11 +47,27 @@ struct ConvTcArgs {
   int cout;
   int num_kc;             // Kp / 64
   int a_stages;
+  int e_pad;              // rows per 64-column panel of the chunk-major h
+  int debug;              // NNCONV_DEBUG bit0: skip the scatter (measurement experiments only)
+  // cross-kernel pipelining (tc05.cuh): Y of this batch must be complete; raise done when all reds are out;
+  // the last kernel of an application also joins every earlier kernel of the chain before it exits
+  const int* wait_ok;
+  int* done_cnt;
+  int* done_ok;
+  const int* join_ok;
+  int join_n;
+};
+
+// tmH.m[i] has a box of 16*(i+1) rows: the last tile of a source group only fetches the rows it owns
+// (rounded up to 16) instead of a full 128-row box that would re-read the next group's rows from HBM
+// (ncu r1a: 233 MB DRAM read per launch for 158 MB of algorithmic bytes).
+struct HMaps {
+  CUtensorMap m[8];
 };
 
 template <int FMT>
 __global__ void __launch_bounds__(192, 1)
-k_conv_tc(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmY, ConvTcArgs a) {
+k_conv_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMap tmY, ConvTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -74,7 +92,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUten
   const uint32_t tmem_cols = a.cout <= 16 ? 32 : a.cout <= 32 ? 64 : a.cout <= 64 ? 128 : a.cout <= 128 ? 256 : 512;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmH);
+    for (int i = 0; i < 8; ++i) prefetch_tmap(&tmH.m[i]);
     prefetch_tmap(&tmY);
     for (int s = 0; s < a.a_stages; ++s) {
       mbar_init(&a_full[s], 1);
@@ -94,6 +112,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUten
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
+  if (a.wait_ok != nullptr && threadIdx.x == 0) flag_wait(a.wait_ok);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -109,6 +129,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUten
       for (int t = t0; t < t1; ++t) {
         const int c = a.tile_c[t];
         const int e0 = a.tile_e0[t];
+        const int box = (a.tile_cnt[t] + 15) >> 4;            // 1..8 -> rows = 16 * box
+        const CUtensorMap* mh = &tmH.m[box - 1];
+        const uint32_t a_bytes = static_cast<uint32_t>(box) * 16u * 128u;
         const bool new_b = c != prev_c;
         for (int j = 0; j < a.num_kc; ++j) {
           if (new_b) {
@@ -117,8 +140,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUten
             tma_load_2d(smem_b + j * b_chunk_stride, &tmY, &b_full[j], j * 64, (c - a.c0) * a.cout, kEvictLast);
           }
           mbar_wait(&a_empty[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&a_full[stage], kATileBytes);
-          tma_load_2d(smem_a + stage * kATileBytes, &tmH, &a_full[stage], j * 64, e0, kEvictFirst);
+          mbar_arrive_expect_tx(&a_full[stage], a_bytes);
+          tma_load_2d(smem_a + stage * kATileBytes, mh, &a_full[stage], 0, j * a.e_pad + e0, kEvictFirst);
           if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
         }
         if (new_b) { ++b_gen; prev_c = c; }
@@ -184,7 +207,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUten
         uint32_t v[16];
         tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * a.cout + cc, v);
         tmem_ld_wait();
-        if (ok) {
+        if (ok && !(a.debug & 1)) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 cq = __ldg(reinterpret_cast<const float4*>(cv + cc) + q);
@@ -200,10 +223,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUten
     }
   }
   fence_before_sync();
-  __syncthreads();
+  if (a.done_cnt != nullptr) signal_done(a.done_cnt, a.done_ok);   // includes __syncthreads
+  else __syncthreads();
   if (warp == 1) {
     fence_after_sync();
     tmem_dealloc(tmem_base, tmem_cols);
+  }
+  if (a.join_ok != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int i = 0; i < a.join_n; ++i) flag_wait(a.join_ok + i);
   }
 }
 
@@ -221,17 +248,23 @@ bool tc_shapes_supported(const Weights* W) {
 
 int launch_conv_tc(int prec, const Plan* P, const void* h, int Kp, const void* Y, int64_t y_nodes, int cout,
                    int tile_begin, int tile_end, int c0, const float* cvec, int aggr_mean, float* out,
-                   cudaStream_t st) {
+                   cudaStream_t st, const PipeFlags* pf) {
   if (tile_end <= tile_begin) return NNCONV_OK;
   int s = tc_init();
   if (s != NNCONV_OK) return s;
   const int bf = prec == PREC_BF16;
-  CUtensorMap tmH, tmY;
-  s = make_tmap_2d_16b(&tmH, bf, h, static_cast<uint64_t>(P->E), static_cast<uint64_t>(Kp), 128);
-  if (s != NNCONV_OK) return s;
+  const int64_t e_pad = round_up64(P->E, 128);
+  HMaps tmH;
+  CUtensorMap tmY;
+  for (int i = 0; i < 8; ++i) {
+    // chunk-major h: [Kp/64 panels][E_pad rows][64 cols] viewed as a 2-D tensor of 64-column rows
+    s = make_tmap_2d_16b(&tmH.m[i], bf, h, static_cast<uint64_t>(Kp / 64) * e_pad, 64, 16 * (i + 1));
+    if (s != NNCONV_OK) return s;
+  }
   s = make_tmap_2d_16b(&tmY, bf, Y, static_cast<uint64_t>(y_nodes) * cout, static_cast<uint64_t>(Kp), cout);
   if (s != NNCONV_OK) return s;
   ConvTcArgs a;
+  a.e_pad = static_cast<int>(e_pad);
   a.tile_c = P->tile_c; a.tile_e0 = P->tile_e0; a.tile_cnt = P->tile_cnt; a.dst_sorted = P->dst_sorted;
   a.inv_deg = aggr_mean ? P->inv_deg : nullptr; a.cvec = cvec; a.out = out;
   a.tile_begin = tile_begin; a.tile_end = tile_end; a.c0 = c0; a.cout = cout; a.num_kc = Kp / 64;
@@ -240,7 +273,10 @@ int launch_conv_tc(int prec, const Plan* P, const void* h, int Kp, const void* Y
   int stages = avail / kATileBytes;
   if (stages > 8) stages = 8;
   NNC_REQUIRE(stages >= 2, NNCONV_ERR_UNSUPPORTED, "conv_tc: Y tile does not fit shared memory (cout=%d Kp=%d)", cout, Kp);
+  if (const char* e = getenv("NNCONV_CONV_STAGES")) { int v = atoi(e); if (v >= 2 && v < stages) stages = v; }
   a.a_stages = stages;
+  a.debug = 0;
+  if (const char* e = getenv("NNCONV_DEBUG")) a.debug = atoi(e);
   const int smem_bytes = a.num_kc * b_stride + stages * kATileBytes + 1024 + 512;
   static int attr_set[2] = {0, 0};
   if (!attr_set[bf]) {
@@ -248,11 +284,25 @@ int launch_conv_tc(int prec, const Plan* P, const void* h, int Kp, const void* Y
     else NNC_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[bf] = 1;
   }
+  a.wait_ok = pf ? pf->wait_ok : nullptr;
+  a.done_cnt = pf ? pf->done_cnt : nullptr;
+  a.done_ok = pf ? pf->done_ok : nullptr;
+  a.join_ok = pf ? pf->join_ok : nullptr;
+  a.join_n = pf ? pf->join_n : 0;
   const int tiles = tile_end - tile_begin;
   const int grid = tiles < tc_num_sms() ? tiles : tc_num_sms();
-  if (bf) k_conv_tc<1><<<grid, 192, smem_bytes, st>>>(tmH, tmY, a);
-  else k_conv_tc<0><<<grid, 192, smem_bytes, st>>>(tmH, tmY, a);
-  NNC_CHECK_LAUNCH();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pf && pf->pdl) ? 1 : 0;
+  if (bf) NNC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<1>, tmH, tmY, a));
+  else NNC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<0>, tmH, tmY, a));
   return NNCONV_OK;
 }
 

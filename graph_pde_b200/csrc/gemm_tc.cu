@@ -4,8 +4,8 @@
 // Linear + ReLU) over a chunk of edges and (b) the per-source matrices
 // Y[c, (o,k)] = sum_i x[c, i] * W_L[i*out + o, k]  (the last Linear reassociated, nn_conv.py:274-275).
 //
-// Structure: persistent CTAs (grid = #SMs), 6 warps: warp 0 = TMA producer (one lane), warp 1 = MMA
-// issuer (one lane) + TMEM allocator, warps 2..5 = epilogue (TMEM -> registers -> bias/ReLU -> 16-bit
+// Structure: persistent CTAs (grid = #SMs), 10 warps: warp 0 = TMA producer (one lane), warp 1 = MMA
+// issuer (one lane) + TMEM allocator, warps 2..9 = epilogue (TMEM -> registers -> bias/ReLU -> 16-bit
 // -> global).  Operands are K-major 128B-swizzled tiles [128 x 64] / [BLOCK_N x 64] staged by TMA in a
 // ring of kStages; accumulators are double buffered in TMEM (2 x BLOCK_N columns) so the epilogue of
 // tile i overlaps the MMAs of tile i+1.
@@ -26,6 +26,15 @@ struct GemmTcArgs {
   int relu;
   void* C;
   int64_t ldc;         // elements
+  // chunk-major output (the layout the contraction kernel streams): element (row, col) lives at
+  // ((col / 64) * chunk_rows_pad + c_row0 + row) * 64 + col % 64, i.e. one contiguous [rows, 64] panel per
+  // 64-column K chunk, so a TMA box of consecutive rows is ONE contiguous block of DRAM.  0 = row-major.
+  int64_t chunk_rows_pad;
+  int64_t c_row0;
+  // optional cross-kernel pipelining (see tc05.cuh): wait for *wait_ok before touching C, raise *done_ok
+  const int* wait_ok;
+  int* done_cnt;
+  int* done_ok;
 };
 
 template <int BLOCK_N>
@@ -41,7 +50,7 @@ struct GemmCfg {
 };
 
 template <int BLOCK_N, int FMT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmTcArgs a) {
   using Cfg = GemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -71,7 +80,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 4);   // one arrive per epilogue warp
+      mbar_init(&tempty[s], 8);   // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -79,6 +88,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
+  if (a.wait_ok != nullptr && threadIdx.x == 0) flag_wait(a.wait_ok);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -131,8 +142,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
     }
   } else {
-    // ---------------------------------------------------------------- epilogue warps 2..5
+    // ---------------------------------------------------------------- epilogue warps 2..9
+    // Two warps per TMEM lane quarter, each owning half of the tile's columns; TMEM loads are software
+    // pipelined (chunk c+1 is in flight while chunk c is converted and stored) -- ncu r1a showed the
+    // 4-warp, load-wait-store epilogue, not the tensor pipe or L2, bounding the K=64 GEMMs.
     const int quarter = warp % 4;     // TMEM lane quarter this warp may access
+    const int half = (warp - 2) / 4;  // which half of the BLOCK_N columns
+    constexpr int kChunks = BLOCK_N / 64;          // 32-column chunks per half
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int mb = t / n_blocks, nb = t % n_blocks;
@@ -142,17 +158,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int row = mb * Cfg::kBlockM + quarter * 32 + lane;
       const bool row_ok = row < a.M;
       uint16_t* crow = reinterpret_cast<uint16_t*>(a.C) + static_cast<int64_t>(row) * a.ldc;
-#pragma unroll 1
-      for (int cc = 0; cc < BLOCK_N / 32; ++cc) {
-        const int col0 = nb * BLOCK_N + cc * 32;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N + cc * 32, v);
-        tmem_ld_wait();
+      const int64_t grow = a.c_row0 + row;
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N +
+                             half * (BLOCK_N / 2);
+      uint32_t v[2][32];
+      tmem_ld32(tbase, v[0]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int cc = 0; cc < kChunks; ++cc) {
+        if (cc + 1 < kChunks) tmem_ld32(tbase + (cc + 1) * 32, v[(cc + 1) & 1]);
+        const int col0 = nb * BLOCK_N + half * (BLOCK_N / 2) + cc * 32;
         if (col0 < a.N && row_ok) {
+          const uint32_t* vv = v[cc & 1];
           uint32_t packed[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
+            float f0 = __uint_as_float(vv[2 * j]), f1 = __uint_as_float(vv[2 * j + 1]);
             if (a.bias) {
               f0 += __ldg(a.bias + col0 + 2 * j);
               f1 += __ldg(a.bias + col0 + 2 * j + 1);
@@ -169,11 +190,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               packed[j] = *reinterpret_cast<uint32_t*>(&h);
             }
           }
-          uint4* dst = reinterpret_cast<uint4*>(crow + col0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          uint16_t* dst = a.chunk_rows_pad > 0
+                              ? reinterpret_cast<uint16_t*>(a.C) +
+                                    (static_cast<int64_t>(col0 >> 6) * a.chunk_rows_pad + grow) * 64 + (col0 & 63)
+                              : crow + col0;
+          st_global_v8(dst, packed);            // 2 x 32 B: full sectors (16 B stores were half-used
+          st_global_v8(dst + 16, packed + 8);   // sectors, ncu r1a)
         }
+        if (cc + 1 < kChunks) tmem_ld_wait();
       }
       fence_before_sync();
       __syncwarp();
@@ -181,7 +205,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   }
   fence_before_sync();
-  __syncthreads();
+  if (a.done_cnt != nullptr) signal_done(a.done_cnt, a.done_ok);   // includes __syncthreads
+  else __syncthreads();
   if (warp == 1) {
     fence_after_sync();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -191,7 +216,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 int g_num_sms = 0;
 
 template <int BLOCK_N, int FMT>
-int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& a, cudaStream_t st) {
+int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& a, cudaStream_t st, bool pdl) {
   using Cfg = GemmCfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -201,8 +226,17 @@ int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTc
   }
   const int tiles = ceil_div(a.M, 128) * ceil_div(a.N, BLOCK_N);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  k_gemm_tc<BLOCK_N, FMT><<<grid, 192, Cfg::kSmemBytes, st>>>(tmA, tmB, a);
-  NNC_CHECK_LAUNCH();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(320);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  NNC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<BLOCK_N, FMT>, tmA, tmB, a));
   return NNCONV_OK;
 }
 
@@ -225,13 +259,15 @@ int tc_init() {
 int tc_num_sms() { return g_num_sms; }
 
 int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a_row0, int M, int K, const void* B,
-                   int N, const float* bias, int relu, void* C, int64_t ldc, cudaStream_t st) {
+                   int N, const float* bias, int relu, void* C, int64_t ldc, cudaStream_t st, const PipeFlags* pf,
+                   int64_t chunk_rows_pad, int64_t c_row0) {
   if (M <= 0 || N <= 0) return NNCONV_OK;
   int s = tc_init();
   if (s != NNCONV_OK) return s;
   NNC_REQUIRE(prec == PREC_F16 || prec == PREC_BF16, NNCONV_ERR_ARG, "gemm_tc: 16-bit precisions only");
   NNC_REQUIRE(K % 64 == 0 && N % 64 == 0 && K >= 64, NNCONV_ERR_ARG, "gemm_tc: K=%d N=%d must be multiples of 64", K, N);
-  NNC_REQUIRE(ldc % 8 == 0, NNCONV_ERR_ARG, "gemm_tc: ldc must be a multiple of 8 elements");
+  NNC_REQUIRE(ldc % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 31) == 0, NNCONV_ERR_ARG,
+              "gemm_tc: C must be 32-byte aligned with ldc a multiple of 16 elements");
   const int bf = prec == PREC_BF16;
   const int BN = (N % 256 == 0 || N > 256) ? 256 : (N % 128 == 0 || N > 128) ? 128 : 64;
   CUtensorMap tmA, tmB;
@@ -241,9 +277,15 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
   if (s != NNCONV_OK) return s;
   GemmTcArgs a;
   a.M = M; a.N = N; a.K = K; a.a_row0 = static_cast<int>(a_row0); a.bias = bias; a.relu = relu; a.C = C; a.ldc = ldc;
-  if (BN == 256) return bf ? launch_gemm_cfg<256, 1>(tmA, tmB, a, st) : launch_gemm_cfg<256, 0>(tmA, tmB, a, st);
-  if (BN == 128) return bf ? launch_gemm_cfg<128, 1>(tmA, tmB, a, st) : launch_gemm_cfg<128, 0>(tmA, tmB, a, st);
-  return bf ? launch_gemm_cfg<64, 1>(tmA, tmB, a, st) : launch_gemm_cfg<64, 0>(tmA, tmB, a, st);
+  a.chunk_rows_pad = chunk_rows_pad;
+  a.c_row0 = c_row0;
+  a.wait_ok = pf ? pf->wait_ok : nullptr;
+  a.done_cnt = pf ? pf->done_cnt : nullptr;
+  a.done_ok = pf ? pf->done_ok : nullptr;
+  const bool pdl = pf && pf->pdl;
+  if (BN == 256) return bf ? launch_gemm_cfg<256, 1>(tmA, tmB, a, st, pdl) : launch_gemm_cfg<256, 0>(tmA, tmB, a, st, pdl);
+  if (BN == 128) return bf ? launch_gemm_cfg<128, 1>(tmA, tmB, a, st, pdl) : launch_gemm_cfg<128, 0>(tmA, tmB, a, st, pdl);
+  return bf ? launch_gemm_cfg<64, 1>(tmA, tmB, a, st, pdl) : launch_gemm_cfg<64, 0>(tmA, tmB, a, st, pdl);
 }
 
 }  // namespace nnc

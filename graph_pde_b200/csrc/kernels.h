@@ -9,7 +9,11 @@ namespace nnc {
 int launch_pad_convert(int prec, const float* src, int R, int C, void* dst, int Rp, int Cp, cudaStream_t st);
 int launch_w3p(int prec, const float* WL, int cin, int cout, int K, int Kp, int cin_p, void* dst, cudaStream_t st);
 int launch_edge_layer1(int prec, const float* edge_attr, const int* perm, int64_t e_begin, int64_t e_count, int k_in,
-                       const float* W1, const float* b1, int kp1, int identity, void* out, cudaStream_t st);
+                       const float* W1, const float* b1, int kp1, int identity, void* out, cudaStream_t st,
+                       int64_t chunk_rows_pad = 0, int64_t out_row0 = 0);
+int launch_build_a1(int prec, const float* edge_attr, const int* perm, int64_t e_begin, int64_t e_count, int k_in,
+                    void* A1, cudaStream_t st);
+int launch_w1aug(int prec, const float* W1, const float* b1, int k1, int kp1, int k_in, void* dst, cudaStream_t st);
 int launch_out_init(const float* x, const float* root, const float* bias, int64_t N, int cin, int cout, float* out,
                     cudaStream_t st);
 int launch_src_prep(int prec, const float* x, const int* src_nodes, int S, int cin, int cin_p, int cout,
@@ -19,15 +23,26 @@ int launch_sgemm_store(const float* A, int64_t lda, const float* B, int64_t ldb,
 int launch_sgemm_scatter(const Plan* P, const float* h, int Kp, const float* Y, int cout, int tile_begin,
                          int tile_end, int c0, const float* cvec, int aggr_mean, float* out, cudaStream_t st);
 
+// Cross-kernel pipelining of one conv application (PDL + completion flags, see tc05.cuh).
+struct PipeFlags {
+  bool pdl;             // launch with programmatic stream serialization
+  const int* wait_ok;   // flag that must be raised before this kernel touches its dependent buffer (or nullptr)
+  int* done_cnt;        // per-kernel CTA counter (or nullptr)
+  int* done_ok;         // raised by the last CTA
+  const int* join_ok;   // conv only: flags [join_n] the LAST kernel of the chain waits for before it exits
+  int join_n;
+};
+
 // ---- gemm_tc.cu (tcgen05): C[M, N] (16-bit) = act(A[M, K] * B[N, K]^T + bias); A rows start at a_row0 of the
 // tensor A_base[a_rows_total, K]; K, N multiples of 64.  bias == nullptr -> no bias, relu flag separate.
 int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a_row0, int M, int K,
-                   const void* B, int N, const float* bias, int relu, void* C, int64_t ldc, cudaStream_t st);
+                   const void* B, int N, const float* bias, int relu, void* C, int64_t ldc, cudaStream_t st,
+                   const PipeFlags* pf = nullptr, int64_t chunk_rows_pad = 0, int64_t c_row0 = 0);
 
 // ---- conv_tc.cu (tcgen05): per-source contraction + scatter for tiles [tile_begin, tile_end)
 int launch_conv_tc(int prec, const Plan* P, const void* h, int Kp, const void* Y, int64_t y_nodes, int cout,
                    int tile_begin, int tile_end, int c0, const float* cvec, int aggr_mean, float* out,
-                   cudaStream_t st);
+                   cudaStream_t st, const PipeFlags* pf = nullptr);
 
 bool tc_shapes_supported(const Weights* W);
 int tc_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes; idempotent

@@ -54,7 +54,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_edge_layer1(const float* __restrict__ edge_attr, const int* __restrict__ perm, int64_t e_begin, int64_t e_count,
               int k_in, const float* __restrict__ W1, const float* __restrict__ b1, int kp1, int identity,
-              T* __restrict__ out) {
+              T* __restrict__ out, int64_t chunk_rows_pad, int64_t out_row0) {
   extern __shared__ float sm[];
   float* s_ea = sm;                       // [kL1Edges][k_in]
   int64_t p0 = static_cast<int64_t>(blockIdx.x) * kL1Edges;
@@ -67,10 +67,14 @@ k_edge_layer1(const float* __restrict__ edge_attr, const int* __restrict__ perm,
     s_ea[i] = edge_attr[src * k_in + c];
   }
   __syncthreads();
+  // row-major [rows, kp1] or chunk-major [kp1/64][chunk_rows_pad][64] (see gemm_tc.cu)
+  auto oidx = [&](int e, int j) -> int64_t {
+    return chunk_rows_pad > 0 ? (static_cast<int64_t>(j >> 6) * chunk_rows_pad + out_row0 + p0 + e) * 64 + (j & 63)
+                              : (p0 + e) * static_cast<int64_t>(kp1) + j;
+  };
   for (int j = threadIdx.x; j < kp1; j += blockDim.x) {
     if (identity) {
-      for (int e = 0; e < ne; ++e)
-        out[(p0 + e) * kp1 + j] = cvt<T>(j < k_in ? s_ea[e * k_in + j] : 0.f);
+      for (int e = 0; e < ne; ++e) out[oidx(e, j)] = cvt<T>(j < k_in ? s_ea[e * k_in + j] : 0.f);
       continue;
     }
     float w[16];
@@ -89,9 +93,69 @@ k_edge_layer1(const float* __restrict__ edge_attr, const int* __restrict__ perm,
       } else {
         for (int c = 0; c < k_in; ++c) acc = fmaf(W1[static_cast<int64_t>(j) * k_in + c], s_ea[e * k_in + c], acc);
       }
-      out[(p0 + e) * kp1 + j] = cvt<T>(fmaxf(acc, 0.f));
+      out[oidx(e, j)] = cvt<T>(fmaxf(acc, 0.f));
     }
   }
+}
+
+// ---- first edge-MLP layer on the tensor cores with fp32-grade inputs -------------------------------
+// v = hi + lo with hi = T(v), lo = T(v - hi): two 16-bit values carry ~22 mantissa bits.  With
+//   A1[p, :] = [hi(ea) | lo(ea) | hi(ea) | 1 | 1 | 0...]            (64 columns, one UMMA K block)
+//   B1[j, :] = [hi(W1_j) | hi(W1_j) | lo(W1_j) | hi(b1_j) | lo(b1_j) | 0...]
+// A1 . B1^T = ea . W1_j + b1_j up to the dropped lo*lo terms (2^-22 relative): the first Linear keeps
+// fp32-grade accuracy although it runs as a 16-bit tcgen05 GEMM (utilities.py:223-227, first layer).
+template <typename T>
+__device__ __forceinline__ float as_float(T v);
+template <>
+__device__ __forceinline__ float as_float<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float as_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void k_build_a1(const float* __restrict__ edge_attr, const int* __restrict__ perm, int64_t e_begin,
+                           int64_t e_count, int k_in, T* __restrict__ A1) {
+  int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;   // one thread per 8 columns
+  int64_t p = idx >> 3;
+  if (p >= e_count) return;
+  int c0 = static_cast<int>(idx & 7) * 8;
+  int64_t src = perm ? perm[e_begin + p] : (e_begin + p);
+  const float* ea = edge_attr + src * k_in;
+  T v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int c = c0 + i;
+    float out = 0.f;
+    if (c < 3 * k_in) {
+      float a = ea[c % k_in];
+      T hi = cvt<T>(a);
+      out = (c >= k_in && c < 2 * k_in) ? (a - as_float<T>(hi)) : as_float<T>(hi);
+    } else if (c < 3 * k_in + 2) {
+      out = 1.f;
+    }
+    v[i] = cvt<T>(out);
+  }
+  *reinterpret_cast<uint4*>(A1 + p * 64 + c0) = *reinterpret_cast<const uint4*>(v);
+}
+
+template <typename T>
+__global__ void k_w1aug(const float* __restrict__ W1, const float* __restrict__ b1, int k1, int kp1, int k_in,
+                        T* __restrict__ dst) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= kp1 * 64) return;
+  int j = idx / 64, c = idx % 64;
+  float out = 0.f;
+  if (j < k1) {
+    if (c < 3 * k_in) {
+      float w = W1[j * k_in + (c % k_in)];
+      T hi = cvt<T>(w);
+      out = (c >= 2 * k_in) ? (w - as_float<T>(hi)) : as_float<T>(hi);
+    } else if (c < 3 * k_in + 2) {
+      float b = b1[j];
+      T hi = cvt<T>(b);
+      out = (c == 3 * k_in) ? as_float<T>(hi) : (b - as_float<T>(hi));
+    }
+  }
+  dst[idx] = cvt<T>(out);
 }
 
 // out[n, o] = bias[o] + sum_i x[n, i] root[i, o]   (graph-neural-operator/nn_conv.py:277-282), or 0
@@ -260,19 +324,41 @@ int launch_w3p(int prec, const float* WL, int cin, int cout, int K, int Kp, int 
 }
 
 int launch_edge_layer1(int prec, const float* edge_attr, const int* perm, int64_t e_begin, int64_t e_count, int k_in,
-                       const float* W1, const float* b1, int kp1, int identity, void* out, cudaStream_t st) {
+                       const float* W1, const float* b1, int kp1, int identity, void* out, cudaStream_t st,
+                       int64_t chunk_rows_pad, int64_t out_row0) {
   if (e_count <= 0) return NNCONV_OK;
   unsigned g = (unsigned)ceil_div64(e_count, kL1Edges);
   size_t sm = sizeof(float) * kL1Edges * k_in;
   if (prec == PREC_FP32)
     k_edge_layer1<float><<<g, 256, sm, st>>>(edge_attr, perm, e_begin, e_count, k_in, W1, b1, kp1, identity,
-                                             static_cast<float*>(out));
+                                             static_cast<float*>(out), chunk_rows_pad, out_row0);
   else if (prec == PREC_F16)
     k_edge_layer1<__half><<<g, 256, sm, st>>>(edge_attr, perm, e_begin, e_count, k_in, W1, b1, kp1, identity,
-                                              static_cast<__half*>(out));
+                                              static_cast<__half*>(out), chunk_rows_pad, out_row0);
   else
     k_edge_layer1<__nv_bfloat16><<<g, 256, sm, st>>>(edge_attr, perm, e_begin, e_count, k_in, W1, b1, kp1, identity,
-                                                     static_cast<__nv_bfloat16*>(out));
+                                                     static_cast<__nv_bfloat16*>(out), chunk_rows_pad, out_row0);
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
+}
+
+int launch_build_a1(int prec, const float* edge_attr, const int* perm, int64_t e_begin, int64_t e_count, int k_in,
+                    void* A1, cudaStream_t st) {
+  if (e_count <= 0) return NNCONV_OK;
+  unsigned g = (unsigned)ceil_div64(e_count * 8, 256);
+  if (prec == PREC_F16)
+    k_build_a1<__half><<<g, 256, 0, st>>>(edge_attr, perm, e_begin, e_count, k_in, static_cast<__half*>(A1));
+  else
+    k_build_a1<__nv_bfloat16><<<g, 256, 0, st>>>(edge_attr, perm, e_begin, e_count, k_in,
+                                                 static_cast<__nv_bfloat16*>(A1));
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
+}
+
+int launch_w1aug(int prec, const float* W1, const float* b1, int k1, int kp1, int k_in, void* dst, cudaStream_t st) {
+  unsigned g = (unsigned)ceil_div(kp1 * 64, 256);
+  if (prec == PREC_F16) k_w1aug<__half><<<g, 256, 0, st>>>(W1, b1, k1, kp1, k_in, static_cast<__half*>(dst));
+  else k_w1aug<__nv_bfloat16><<<g, 256, 0, st>>>(W1, b1, k1, kp1, k_in, static_cast<__nv_bfloat16*>(dst));
   NNC_CHECK_LAUNCH();
   return NNCONV_OK;
 }

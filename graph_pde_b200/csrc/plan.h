@@ -44,6 +44,7 @@ struct Weights {
   size_t esize;                 // bytes per element of activations / tensor-core operands
   const float* W1;              // [kp[1], k_in] fp32 (zero padded rows); nullptr when n_layers == 1
   const float* b1;              // [kp[1]]
+  const void* W1aug;            // [kp[1], 64] in `prec`: split hi/lo first layer incl. bias (tensor-core path), or nullptr
   const void* Wh[kMaxLayers];   // hidden layers l = 2 .. L-1: [kp[l], kp[l-1]] in `prec`
   const float* bh[kMaxLayers];  // [kp[l]] fp32
   const void* W3p;              // [cout*Kp, cin_p] in `prec`:  W3p[(o*Kp + k), i] = W_L[i*cout + o, k]

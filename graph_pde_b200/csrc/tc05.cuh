@@ -154,4 +154,49 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
+// 256-bit global store (sm_100+): one full 32-byte sector per thread per instruction.
+__device__ __forceinline__ void st_global_v8(void* addr, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
+// ---------------------------------------------------------------- cross-kernel pipelining (PDL + flags)
+// Kernels of one NNConv application are launched with programmatic stream serialization: a kernel may
+// start as soon as every CTA of its predecessor has executed launch_dependents, i.e. CTAs of kernel k+1
+// fill SMs as CTAs of kernel k retire (no grid-wide drain between the many small launches).  Real data
+// dependencies are carried by completion flags in global memory (release/acquire at gpu scope).
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// one thread: wait until *ok != 0 (bounded), then order later async-proxy (TMA) reads after it
+__device__ __forceinline__ void flag_wait(const int* ok) {
+#pragma unroll 1
+  for (uint32_t i = 0; i < (1u << 26); ++i) {
+    if (ld_acquire(ok) != 0) {
+      asm volatile("fence.proxy.async;" ::: "memory");
+      return;
+    }
+    __nanosleep(64);
+  }
+  __trap();
+}
+// call with ALL threads of the CTA after its last global write: the last CTA of the grid raises *ok
+__device__ __forceinline__ void signal_done(int* cnt, int* ok) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(cnt, 1);
+    if (prev == static_cast<int>(gridDim.x) - 1) {
+      __threadfence();
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ok), "r"(1) : "memory");
+    }
+  }
+}
+
 }  // namespace tc05

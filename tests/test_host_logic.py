@@ -1,0 +1,113 @@
+"""CPU-only tests of the host-side mirror of the reference interface (no kernels run)."""
+import math
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from graph_pde_b200 import graphs
+from graph_pde_b200.models import DenseNet, KernelInduced, KernelNN, MGKN, MKGN
+from graph_pde_b200.nn_conv import NNConv, NNConv_old, _linear_chain
+from oracle import nnconv_oracle as O
+from tests.helpers import GOLDEN
+
+
+def test_signature_attributes_repr_and_state_dict_keys():
+    mlp = DenseNet([6, 16, 16, 64], torch.nn.ReLU)
+    conv = NNConv_old(8, 8, mlp, aggr='mean')
+    assert repr(conv) == 'NNConv_old(8, 8)'                  # nn_conv.py:284-286
+    assert (conv.in_channels, conv.out_channels, conv.aggr) == (8, 8, 'mean')
+    assert sorted(conv.state_dict().keys()) == sorted(
+        ['root', 'bias'] + ['nn.layers.%d.%s' % (i, n) for i in (0, 2, 4) for n in ('weight', 'bias')])
+    conv2 = NNConv(8, 8, DenseNet([6, 16, 64], torch.nn.ReLU), aggr='mean', root_weight=False, bias=False)
+    assert conv2.root is None and conv2.bias is None
+    assert repr(conv2) == 'NNConv(8, 8)'
+    with pytest.raises(ValueError):
+        NNConv_old(8, 8, mlp, aggr='median')
+
+
+def test_reset_parameters_matches_reference_stream():
+    """Same RNG consumption order as DenseNet ctor + NNConv_old.reset_parameters (nn_conv.py:261-265)."""
+    torch.manual_seed(0)
+    conv = NNConv_old(32, 32, DenseNet([6, 64, 64, 1024], torch.nn.ReLU), aggr='mean')
+    ws, bs, root, bias = O.reference_init(32, 32, [6, 64, 64, 1024], seed=0)
+    lin = _linear_chain(conv.nn)
+    for l, w, b in zip(lin, ws, bs):
+        assert torch.equal(l.weight.detach(), w) and torch.equal(l.bias.detach(), b)
+    assert torch.equal(conv.root.detach(), root) and torch.equal(conv.bias.detach(), bias)
+    assert float(conv.root.detach().abs().max()) <= 1 / math.sqrt(32)
+
+
+def test_whole_module_pickle_roundtrip(tmp_path):
+    """The reference saves whole modules with torch.save(model) (UAI1_full_resolution.py:317)."""
+    model = KernelNN(8, 16, 2, 6, in_width=6)
+    p = tmp_path / 'm.pt'
+    torch.save(model, p)
+    back = torch.load(p, weights_only=False)
+    assert isinstance(back.conv1, NNConv_old) and back.depth == 2
+    for a, b in zip(model.state_dict().values(), back.state_dict().values()):
+        assert torch.equal(a, b)
+
+
+def test_checkpoint_state_dict_loads_into_our_kernelnn():
+    g = np.load(os.path.join(GOLDEN, 'g3_checkpoint_grain_new.npz'))
+    st = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('w/')}
+    mlp = DenseNet([6, 64, 128, 4096], torch.nn.ReLU)
+    conv = NNConv_old(64, 64, mlp, aggr='mean')
+    conv.load_state_dict({k[len('conv1.'):]: v for k, v in st.items() if k.startswith('conv1.')})
+    assert torch.equal(conv.nn.layers[4].weight.detach(), st['conv1.nn.layers.4.weight'])
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    conv = NNConv_old(8, 8, DenseNet([6, 16, 64], torch.nn.ReLU), aggr='mean')
+    x = torch.randn(10, 8)
+    ei = torch.randint(0, 10, (2, 30))
+    ea = torch.randn(30, 6)
+    with torch.no_grad(), pytest.raises(RuntimeError, match='no CPU path'):
+        conv(x, ei, ea)
+
+
+def test_unsupported_edge_network_is_rejected():
+    bad = torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.Tanh(), torch.nn.Linear(16, 64))
+    with pytest.raises(NotImplementedError):
+        _linear_chain(bad)
+    with pytest.raises(NotImplementedError):
+        _linear_chain(torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU()))
+
+
+def test_model_constructors_match_reference_layouts():
+    g = np.load(os.path.join(GOLDEN, 'g4_mgkn_vcycle.npz'))
+    pts = [int(p) for p in g['points']]
+    ki = KernelInduced(width=32, ker_width=64, depth=2, ker_in=6, points=pts, level=len(pts), in_width=6)
+    ref_keys = sorted(k[len('neurips1/w/'):] for k in g.files if k.startswith('neurips1/w/'))
+    assert sorted(ki.state_dict().keys()) == ref_keys
+    for k in ref_keys:
+        assert tuple(ki.state_dict()[k].shape) == g['neurips1/w/' + k].shape, k
+    mk = MKGN(width=32, ker_width=64, depth=2, ker_in=6, points=pts, level=len(pts), in_width=6)
+    ref_keys = sorted(k[len('general/w/'):] for k in g.files if k.startswith('general/w/'))
+    assert sorted(mk.state_dict().keys()) == ref_keys
+    g5 = np.load(os.path.join(GOLDEN, 'g5_mgkn_burgers1d.npz'))
+    mg = MGKN(width=32, ker_width=64, depth=2, ker_in=4, in_width=2, s=int(g5['s']))
+    ref_keys = sorted(k[2:] for k in g5.files if k.startswith('w/'))
+    assert sorted(mg.state_dict().keys()) == ref_keys
+    for k in ref_keys:
+        assert tuple(mg.state_dict()[k].shape) == g5['w/' + k].shape, k
+
+
+def test_graph_builder_matches_oracle_and_sklearn_golden():
+    g = np.load(os.path.join(GOLDEN, 'g6_ball_graphs.npz'))
+    for key in [k for k in g.files if k.startswith('ei/')]:
+        s, r = key[3:].split('_')
+        s, r = int(s), float(r)
+        ei = graphs.ball_connectivity(s, r)
+        np.testing.assert_array_equal(ei.numpy(), g[key].astype(np.int64))
+        th = torch.arange(s * s, dtype=torch.float64) * 0.01
+        ea = graphs.ball_edge_attr(graphs.square_grid(s), ei, th)
+        np.testing.assert_allclose(ea.numpy(), g['ea/' + key[3:]], atol=1e-6)
+    part = graphs.ball_connectivity(31, 0.1, nodes=(100, 140))
+    full = graphs.ball_connectivity(31, 0.1)
+    sel = (full[0] >= 100) & (full[0] < 140)
+    assert torch.equal(part, full[:, sel])
+    assert full.size(1) == 25673                                # ties-in rule
