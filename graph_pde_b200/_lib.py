@@ -22,7 +22,7 @@ SYMBOLS = [
     'nnconv_plan_destroy', 'nnconv_plan_info', 'nnconv_weights_sizes', 'nnconv_weights_create',
     'nnconv_weights_destroy', 'nnconv_weights_tc_supported', 'nnconv_edge_features_sizes',
     'nnconv_edge_features', 'nnconv_apply_sizes', 'nnconv_apply', 'nnconv_gemm_16b',
-    'nnconv_profile_begin', 'nnconv_profile_end',
+    'nnconv_profile_begin', 'nnconv_profile_end', 'nnconv_debug_trace_dump',
 ]
 
 
@@ -76,6 +76,7 @@ def lib():
     L.nnconv_apply.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_sz, c_vp, P(c_i64)]
     L.nnconv_gemm_16b.argtypes = [c_int, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp]
     L.nnconv_profile_end.argtypes = [P(ctypes.c_double), P(c_i64), c_int]
+    L.nnconv_debug_trace_dump.argtypes = [P(ctypes.c_ulonglong), ctypes.c_uint, P(ctypes.c_uint)]
     for name in SYMBOLS:
         getattr(L, name)
     _lib = L

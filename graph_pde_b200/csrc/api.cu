@@ -356,12 +356,12 @@ int apply(const Plan* P, const Weights* W, const void* h, const float* x, const 
     const int nb = static_cast<int>((P->n_src - c0) < nb_max ? (P->n_src - c0) : nb_max);
     PipeFlags pf{};
     pf.pdl = pipe && b > 0;
+    pf.small_footprint = true;
     pf.wait_ok = (pipe && b >= 3) ? okC + (b - 3) : nullptr;
     pf.done_cnt = pipe ? cntY + b : nullptr;
     pf.done_ok = pipe ? okY + b : nullptr;
     ProfScope ps(PK_Y_GEMM, st);
-    return launch_gemm_tc(W->prec, Xc, P->n_src, c0, nb, W->cin_p, W->W3p, NY, nullptr, 0, Ybuf[b % 3], NY, st,
-                          pipe ? &pf : nullptr);
+    return launch_gemm_tc(W->prec, Xc, P->n_src, c0, nb, W->cin_p, W->W3p, NY, nullptr, 0, Ybuf[b % 3], NY, st, &pf);
   };
   auto launch_c = [&](int64_t b) -> int {
     const int64_t c0 = b * nb_max;
@@ -549,6 +549,11 @@ int nnconv_profile_end(double* ms_by_kind, int64_t* launches_by_kind, int n_kind
   }
   nnc::g_prof.clear();
   return NNCONV_OK;
+}
+
+int nnconv_debug_trace_dump(unsigned long long* host_rec, unsigned int max_rec, unsigned int* n_out) {
+  NNC_REQUIRE(host_rec && n_out, NNCONV_ERR_ARG, "null pointer");
+  return trace_dump(host_rec, max_rec, n_out);
 }
 
 int nnconv_gemm_16b(int precision, const void* A, int64_t M, int K, const void* B, int N, const float* bias,

@@ -35,24 +35,29 @@ struct GemmTcArgs {
   const int* wait_ok;
   int* done_cnt;
   int* done_ok;
+  TraceBuf trace;
+  unsigned int trace_seq;
 };
 
-template <int BLOCK_N>
+// SMALL = 1: a 3-stage, BLOCK_N = 128 footprint (97 KB smem, 256 TMEM columns) that can share an SM with a
+// contraction CTA or a second GEMM CTA -- used for the per-source Y GEMM, which is store bound and runs
+// concurrently with the contraction of the previous batch.
+template <int BLOCK_N, int SMALL = 0>
 struct GemmCfg {
   static constexpr int kBlockM = 128;
   static constexpr int kBlockK = 64;
   static constexpr int kABytes = kBlockM * kBlockK * 2;
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+  static constexpr int kStages = SMALL ? 3 : ((196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes));
   static constexpr int kTmemCols = 2 * BLOCK_N;   // power of two >= 32 for BLOCK_N in {64,128,256}
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N, int FMT>
-__global__ void __launch_bounds__(320, 1)
+template <int BLOCK_N, int FMT, int SMALL>
+__global__ void __launch_bounds__(320, SMALL ? 2 : 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmTcArgs a) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, SMALL>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -88,8 +93,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tmem_alloc(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  const unsigned long long tr0 = a.trace.rec ? gtime() : 0ull;
   pdl_launch_dependents();
   if (a.wait_ok != nullptr && threadIdx.x == 0) flag_wait(a.wait_ok);
+  const unsigned long long tr1 = a.trace.rec ? gtime() : 0ull;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -207,6 +214,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   fence_before_sync();
   if (a.done_cnt != nullptr) signal_done(a.done_cnt, a.done_ok);   // includes __syncthreads
   else __syncthreads();
+  if (threadIdx.x == 0) trace_write(a.trace, (100u + (a.K > 64 ? 1u : 0u)) | (a.trace_seq << 12), tr0, tr1, a.trace.rec ? gtime() : 0ull);
   if (warp == 1) {
     fence_after_sync();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -215,17 +223,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
 int g_num_sms = 0;
 
-template <int BLOCK_N, int FMT>
+template <int BLOCK_N, int FMT, int SMALL>
 int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& a, cudaStream_t st, bool pdl) {
-  using Cfg = GemmCfg<BLOCK_N>;
+  using Cfg = GemmCfg<BLOCK_N, SMALL>;
   static bool attr_set = false;
   if (!attr_set) {
-    NNC_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NNC_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, FMT, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
     attr_set = true;
   }
   const int tiles = ceil_div(a.M, 128) * ceil_div(a.N, BLOCK_N);
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  const int max_ctas = SMALL ? 2 * g_num_sms : g_num_sms;
+  const int grid = tiles < max_ctas ? tiles : max_ctas;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(320);
@@ -236,7 +245,7 @@ int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTc
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  NNC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<BLOCK_N, FMT>, tmA, tmB, a));
+  NNC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<BLOCK_N, FMT, SMALL>, tmA, tmB, a));
   return NNCONV_OK;
 }
 
@@ -269,7 +278,8 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
   NNC_REQUIRE(ldc % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 31) == 0, NNCONV_ERR_ARG,
               "gemm_tc: C must be 32-byte aligned with ldc a multiple of 16 elements");
   const int bf = prec == PREC_BF16;
-  const int BN = (N % 256 == 0 || N > 256) ? 256 : (N % 128 == 0 || N > 128) ? 128 : 64;
+  const bool small = pf && pf->small_footprint && N >= 128;
+  const int BN = small ? 128 : (N % 256 == 0 || N > 256) ? 256 : (N % 128 == 0 || N > 128) ? 128 : 64;
   CUtensorMap tmA, tmB;
   s = make_tmap_2d_16b(&tmA, bf, A_base, static_cast<uint64_t>(a_rows_total), static_cast<uint64_t>(K), 128);
   if (s != NNCONV_OK) return s;
@@ -279,13 +289,20 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
   a.M = M; a.N = N; a.K = K; a.a_row0 = static_cast<int>(a_row0); a.bias = bias; a.relu = relu; a.C = C; a.ldc = ldc;
   a.chunk_rows_pad = chunk_rows_pad;
   a.c_row0 = c_row0;
+  {
+    TraceHandle th = trace_get();
+    static unsigned int launch_seq = 0;
+    a.trace = TraceBuf{th.rec, th.count, th.cap};
+    a.trace_seq = launch_seq++;
+  }
   a.wait_ok = pf ? pf->wait_ok : nullptr;
   a.done_cnt = pf ? pf->done_cnt : nullptr;
   a.done_ok = pf ? pf->done_ok : nullptr;
   const bool pdl = pf && pf->pdl;
-  if (BN == 256) return bf ? launch_gemm_cfg<256, 1>(tmA, tmB, a, st, pdl) : launch_gemm_cfg<256, 0>(tmA, tmB, a, st, pdl);
-  if (BN == 128) return bf ? launch_gemm_cfg<128, 1>(tmA, tmB, a, st, pdl) : launch_gemm_cfg<128, 0>(tmA, tmB, a, st, pdl);
-  return bf ? launch_gemm_cfg<64, 1>(tmA, tmB, a, st, pdl) : launch_gemm_cfg<64, 0>(tmA, tmB, a, st, pdl);
+  if (small) return bf ? launch_gemm_cfg<128, 1, 1>(tmA, tmB, a, st, pdl) : launch_gemm_cfg<128, 0, 1>(tmA, tmB, a, st, pdl);
+  if (BN == 256) return bf ? launch_gemm_cfg<256, 1, 0>(tmA, tmB, a, st, pdl) : launch_gemm_cfg<256, 0, 0>(tmA, tmB, a, st, pdl);
+  if (BN == 128) return bf ? launch_gemm_cfg<128, 1, 0>(tmA, tmB, a, st, pdl) : launch_gemm_cfg<128, 0, 0>(tmA, tmB, a, st, pdl);
+  return bf ? launch_gemm_cfg<64, 1, 0>(tmA, tmB, a, st, pdl) : launch_gemm_cfg<64, 0, 0>(tmA, tmB, a, st, pdl);
 }
 
 }  // namespace nnc

@@ -23,9 +23,20 @@ int launch_sgemm_store(const float* A, int64_t lda, const float* B, int64_t ldb,
 int launch_sgemm_scatter(const Plan* P, const float* h, int Kp, const float* Y, int cout, int tile_begin,
                          int tile_end, int c0, const float* cvec, int aggr_mean, float* out, cudaStream_t st);
 
+// CTA timeline tracing (NNCONV_TRACE=1; measurement only).  The buffer is the one place where the library
+// allocates device memory itself, and only when tracing is requested.
+struct TraceHandle {
+  unsigned long long* rec;
+  unsigned int* count;
+  unsigned int cap;
+};
+TraceHandle trace_get();          // {nullptr,..} when tracing is off
+int trace_dump(unsigned long long* host_rec, unsigned int max_rec, unsigned int* n_out);
+
 // Cross-kernel pipelining of one conv application (PDL + completion flags, see tc05.cuh).
 struct PipeFlags {
   bool pdl;             // launch with programmatic stream serialization
+  bool small_footprint; // GEMM only: 97 KB / 256 TMEM column configuration that can share an SM
   const int* wait_ok;   // flag that must be raised before this kernel touches its dependent buffer (or nullptr)
   int* done_cnt;        // per-kernel CTA counter (or nullptr)
   int* done_ok;         // raised by the last CTA

@@ -199,4 +199,36 @@ __device__ __forceinline__ void signal_done(int* cnt, int* ok) {
   }
 }
 
+// ---------------------------------------------------------------- optional CTA timeline tracing
+// (NNCONV_TRACE=1, measurement only): one record per CTA = {kernel tag, blockIdx, smid, start, ready, end}
+// in nanoseconds of %globaltimer; `ready` = after the cross-kernel flag wait.
+struct TraceBuf {
+  unsigned long long* rec;   // [cap][6]
+  unsigned int* count;
+  unsigned int cap;
+};
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned int smid() {
+  unsigned int r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void trace_write(const TraceBuf& tb, unsigned int tag, unsigned long long t0,
+                                            unsigned long long t1, unsigned long long t2) {
+  if (tb.rec == nullptr) return;
+  const unsigned int i = atomicAdd(tb.count, 1u);
+  if (i >= tb.cap) return;
+  unsigned long long* r = tb.rec + static_cast<size_t>(i) * 6;
+  r[0] = tag;
+  r[1] = blockIdx.x;
+  r[2] = smid();
+  r[3] = t0;
+  r[4] = t1;
+  r[5] = t2;
+}
+
 }  // namespace tc05

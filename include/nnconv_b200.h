@@ -115,6 +115,11 @@ int nnconv_apply(const nnconv_plan_t* plan, const nnconv_weights_t* w, const voi
 int nnconv_profile_begin(void);
 int nnconv_profile_end(double* ms_by_kind, int64_t* launches_by_kind, int n_kinds);
 
+/* ---- debugging aid: with NNCONV_TRACE=1 in the environment every tcgen05 CTA records
+ * {tag, blockIdx, smid, t_start, t_ready, t_end} (globaltimer ns); this copies the records to the host and
+ * clears the buffer.  tag: 100 = K=64 GEMM, 101 = hidden GEMM, 200 = contraction. */
+int nnconv_debug_trace_dump(unsigned long long* host_rec, unsigned int max_rec, unsigned int* n_out);
+
 /* ---- unit-test hook for the tcgen05 GEMM used by the hidden layers and the per-source matrices:
  * C[M,N] (16-bit) = act(A[M,K] * B[N,K]^T + bias); K, N multiples of 64; bias nullable. ------------- */
 int nnconv_gemm_16b(int precision, const void* A, int64_t M, int K, const void* B, int N, const float* bias,

@@ -1,0 +1,84 @@
+"""GPU parity of the CALLERS: our KernelNN / KernelInduced / MKGN / MGKN modules,
+loaded with the reference modules' parameters, against golden outputs produced by the reference's own model
+classes (oracle/gen_golden.py).  pytest -m gpu."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import GOLDEN, TOL, cfg1_weights, ei64, rel_err, t
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+class _Data(object):
+    pass
+
+
+def _load(model, state):
+    model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in state.items()})
+    return model.to(DEV).eval()
+
+
+@pytest.mark.parametrize('precision', ['f16', 'fp32'])
+def test_kernelnn_full_forward_cfg1(precision):
+    from graph_pde_b200.models import KernelNN
+    g = np.load(os.path.join(GOLDEN, 'g2_cfg1_ball16.npz'))
+    fc1, ws, bs, root, bias = cfg1_weights(g)
+    model = KernelNN(32, 1024, 4, 6, in_width=6, precision=precision)
+    st = model.state_dict()
+    st['fc1.weight'], st['fc1.bias'] = fc1.weight.detach(), fc1.bias.detach()
+    for i, l in enumerate((0, 2, 4)):
+        st['conv1.nn.layers.%d.weight' % l], st['conv1.nn.layers.%d.bias' % l] = ws[i], bs[i]
+    st['conv1.root'], st['conv1.bias'] = root, bias
+    st['fc2.weight'], st['fc2.bias'] = t(g['w/fc2.weight']), t(g['w/fc2.bias'])
+    model.load_state_dict(st)
+    model = model.to(DEV).eval()
+    d = _Data()
+    d.x, d.edge_index, d.edge_attr = t(g['node_x']).to(DEV), ei64(g['edge_index']).to(DEV), t(g['edge_attr']).to(DEV)
+    with torch.no_grad():
+        out = model(d)
+    assert rel_err(out, t(g['model_out'])) < TOL[precision]
+
+
+@pytest.mark.parametrize('variant', ['neurips1', 'general'])
+@pytest.mark.parametrize('precision', ['f16', 'fp32'])
+def test_mgkn_vcycle(variant, precision):
+    from graph_pde_b200.models import KernelInduced, MKGN
+    g = np.load(os.path.join(GOLDEN, 'g4_mgkn_vcycle.npz'))
+    pts = [int(p) for p in g['points']]
+    cls = KernelInduced if variant == 'neurips1' else MKGN
+    model = cls(width=32, ker_width=64, depth=2, ker_in=6, points=pts, level=len(pts), in_width=6,
+                precision=precision)
+    pre = variant + '/w/'
+    model = _load(model, {k[len(pre):]: g[k] for k in g.files if k.startswith(pre)})
+    d = _Data()
+    d.x = t(g['node_x']).to(DEV)
+    for nm in ('mid', 'down', 'up'):
+        setattr(d, 'edge_index_' + nm, ei64(g['edge_index_' + nm]).to(DEV))
+        setattr(d, 'edge_attr_' + nm, t(g['edge_attr_' + nm]).to(DEV))
+    d.edge_index_range = torch.from_numpy(g['range_mid']).to(DEV)
+    d.edge_index_down_range = torch.from_numpy(g['range_down']).to(DEV)
+    d.edge_index_up_range = torch.from_numpy(g['range_up']).to(DEV)
+    with torch.no_grad():
+        out = model(d)
+        out2 = model(d)                       # second call: plans / edge features come from the caches
+    assert rel_err(out, t(g[variant + '/out'])) < TOL[precision]
+    assert rel_err(out2, t(g[variant + '/out'])) < TOL[precision]
+
+
+@pytest.mark.parametrize('precision', ['f16', 'fp32'])
+def test_mgkn_orthogonal_burgers1d(precision):
+    from graph_pde_b200.models import MGKN
+    g = np.load(os.path.join(GOLDEN, 'g5_mgkn_burgers1d.npz'))
+    model = MGKN(width=32, ker_width=64, depth=2, ker_in=4, in_width=2, s=int(g['s']), precision=precision)
+    model = _load(model, {k[2:]: g[k] for k in g.files if k.startswith('w/')})
+    n = int(g['n_edge_sets'])
+    X = [t(g['X/%d' % l]).to(DEV) for l in range(int(g['n_levels']))]
+    eis = [ei64(g['edge_index/%d' % i]).to(DEV) for i in range(n)]
+    eas = [t(g['edge_attr/%d' % i]).to(DEV) for i in range(n)]
+    with torch.no_grad():
+        out = model((X, None, eis, eas))
+    assert rel_err(out, t(g['out'])) < TOL[precision]
