@@ -38,7 +38,7 @@ WORKLOADS = {
     # BASELINE.json configs[0] (CPU-runnable case)
     'darcy16': dict(s=16, r=0.25, width=32, ker_width=1024, depth=4),
 }
-KIND_NAMES = ['edge_layer1', 'hidden_gemm', 'node_prologue', 'y_gemm', 'conv_scatter']
+KIND_NAMES = ['edge_layer1', 'hidden_gemm', 'node_prologue', 'y_gemm', 'conv_scatter', 'apply_fused']
 
 
 def peaks():
@@ -277,7 +277,7 @@ def main():
         ms_k = (ctypes.c_double * 8)()
         n_k = (ctypes.c_int64 * 8)()
         _lib.check(L.nnconv_profile_end(ms_k, n_k, 8))
-        prof = {KIND_NAMES[k]: dict(ms=ms_k[k], launches=int(n_k[k])) for k in range(5)}
+        prof = {KIND_NAMES[k]: dict(ms=ms_k[k], launches=int(n_k[k])) for k in range(6)}
     barrier()
 
     if rank == 0:
@@ -286,10 +286,12 @@ def main():
         es = 4 if args.precision == 'fp32' else 2
         conv_bytes = T * E * (Kp * es + 4)                       # h_e stream + dst index, per step
         gemm_flops = 2.0 * E * Kp * Kp                           # hidden layer 2 (1024 x 1024) per step
-        conv_ms, gemm_ms = prof['conv_scatter']['ms'], prof['hidden_gemm']['ms']
-        rf_conv = dict(kernel='k_conv_tc', bound='hbm', achieved=conv_bytes / (conv_ms * 1e-3) / 1e9 if conv_ms else None,
+        fused = prof['apply_fused']['launches'] > 0
+        conv_key = 'apply_fused' if fused else 'conv_scatter'
+        conv_ms, gemm_ms = prof[conv_key]['ms'], prof['hidden_gemm']['ms']
+        rf_conv = dict(kernel='k_apply_tc (Y GEMM + contraction/scatter, persistent)' if fused else 'k_conv_tc', bound='hbm', achieved=conv_bytes / (conv_ms * 1e-3) / 1e9 if conv_ms else None,
                        peak=pk['hbm_gbs'], unit='GB/s', traffic=None,
-                       ms_per_launch=conv_ms / max(1, prof['conv_scatter']['launches']),
+                       ms_per_launch=conv_ms / max(1, prof[conv_key]['launches']),
                        alg_bytes_per_edge_app=Kp * es + 4)
         rf_gemm = dict(kernel='k_gemm_tc(hidden)', bound='tensor', achieved=gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None,
                        peak=pk['tf_sustained'], unit='TFLOP/s', traffic=None,

@@ -326,13 +326,38 @@ int apply(const Plan* P, const Weights* W, const void* h, const float* x, const 
     return NNCONV_OK;
   }
 
-  // Tensor-core path.  Batches of sources sized so that two Y buffers stay L2 resident; kernel order
+  // Tensor-core path, default: ONE persistent kernel per application (apply_tc.cu) in which every CTA runs
+  // the Y GEMM pipeline and the contraction pipeline concurrently over a ring of L2-resident Y batches.
+  const bool no_fuse_env = getenv("NNCONV_NO_FUSE") != nullptr;      // measurement / debugging knob
+  if (!no_fuse_env && apply_fused_supported(W)) {
+    int ring = 4;
+    if (const char* e = getenv("NNCONV_RING")) { int v = atoi(e); if (v >= 2 && v <= 8) ring = v; }
+    if (nodes_cap < ring) ring = nodes_cap >= 2 ? static_cast<int>(nodes_cap) : 1;
+    int64_t nb = nodes_cap / ring;
+    if (nb >= 128) nb = nb / 128 * 128;
+    if (nb > P->n_src) nb = P->n_src;
+    if (ceil_div64(P->n_src, nb) <= kMaxPipeBatches && ring >= 2) {
+      int* flags = reinterpret_cast<int*>(base + L.off_flags);
+      NNC_CHECK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 4 * kMaxPipeBatches, st));
+      {
+        ProfScope ps(PK_APPLY_FUSED, st);
+        s = launch_apply_tc(W->prec, P, W, h, Xc, Y, static_cast<int>(nb), ring, cvec, aggr_mean, out, flags,
+                            kMaxPipeBatches, st);
+      }
+      if (s) return s;
+      if (launches) ++*launches;
+      return NNCONV_OK;
+    }
+  }
+
+  // Fallback (NNCONV_NO_FUSE=1 or shapes the fused kernel does not cover): one Y GEMM + one contraction
+  // kernel per batch of sources.  Batches of sources sized so that the Y buffers stay L2 resident; kernel order
   //   Y(0), Y(1), C(0), Y(2), C(1), ..., C(B-1)            (three Y buffers, b mod 3)
   // launched with programmatic stream serialization, so CTAs of the next kernel start on SMs as CTAs of
   // the running kernel retire; the true dependencies  C(b) <- Y(b)  and  Y(b) <- C(b-3) (buffer reuse)
   // are completion flags in global memory.  Profiling mode (events between kernels) falls back to plain
   // stream order so that per-kernel times are meaningful.
-  static const bool no_pipe_env = getenv("NNCONV_NO_PIPE") != nullptr;   // measurement / debugging knob
+  const bool no_pipe_env = getenv("NNCONV_NO_PIPE") != nullptr;   // measurement / debugging knob
   const bool pipe = !prof_enabled() && !no_pipe_env && nodes_cap >= 3;
   int64_t nb_max = pipe ? nodes_cap / 3 : nodes_cap;
   if (nb_max > P->n_src) nb_max = P->n_src;

@@ -1,0 +1,519 @@
+// One persistent kernel per NNConv application (tensor-core path): the per-source Y GEMM and the per-edge
+// contraction + scatter run CONCURRENTLY inside every CTA as two independent warp-specialised pipelines,
+// coupled only through completion flags in global memory and a ring of Y batches that lives in L2.
+//
+// Why (measured, profiles/r1c_trace_*.md): with one launch per batch of sources (the batch must be small for
+// Y to stay L2 resident) every CTA streamed only ~3 tiles per launch and spent as long ramping up / draining
+// as streaming; PDL overlapped the launches but not the per-CTA ramps.  Here a CTA never drains: its
+// contraction pipeline walks batch after batch (its share of each batch's tiles), while its Y pipeline
+// produces the batches ahead.
+//
+//   roles (12 warps):  0 conv TMA producer | 1 conv MMA issuer (+TMEM owner) | 2-5 conv epilogue (scatter)
+//                      6 Y   TMA producer | 7 Y   MMA issuer               | 8-11 Y epilogue (fp16 stores)
+//   TMEM (512 cols):   [0,256) contraction accumulators 2 stages x kTU tiles x out | [256,512) Y 2 x 128
+//   flags per batch b: okY[b]  raised when all 4*grid Y-epilogue warps finished batch b   (conv waits)
+//                      okC[b]  raised when all grid CTAs consumed batch b                 (Y waits okC[b-ring])
+//
+// Math and data movement of the two pipelines are those of conv_tc.cu and gemm_tc.cu.
+#include <cstdlib>
+
+#include "kernels.h"
+#include "tc05.cuh"
+#include "tmap.h"
+
+namespace nnc {
+
+int tc_num_sms();
+
+namespace {
+
+using namespace tc05;
+
+constexpr int kMaxSlots = 16;
+constexpr int kMaxAStages = 8;
+constexpr int kTU = 2;
+constexpr int kATileBytes = 128 * 64 * 2;
+constexpr int kYBlockN = 128;
+constexpr int kYStageBytes = kATileBytes + kYBlockN * 64 * 2;   // Xc tile + W3p tile
+constexpr int kYStages = 2;
+constexpr int kThreads = 384;
+
+struct ApplyArgs {
+  // plan
+  const int* tile_c;
+  const int* tile_e0;
+  const int* tile_cnt;
+  const int* tile_ptr;    // device [S+1]
+  const int* dst_sorted;
+  const float* inv_deg;   // nullptr -> aggr = add
+  const float* cvec;      // [S, cout]
+  float* out;             // [N, cout]
+  int n_src, nb, n_batches, ring;
+  int cout, nb_slots, passes, a_stages, e_pad;
+  // Y GEMM
+  int NY;                 // cout * Kp
+  int num_kx;             // cin_p / 64
+  void* Yring;            // [ring * nb, NY] 16-bit
+  int* cntY;
+  int* okY;
+  int* cntC;
+  int* okC;
+  TraceBuf trace;
+};
+
+struct HMaps {
+  CUtensorMap m[8];
+};
+
+struct Unit {
+  int t, u, c;
+};
+__device__ __forceinline__ bool next_unit(const ApplyArgs& a, int t1, int& t, Unit& un) {
+  if (t >= t1) return false;
+  un.t = t;
+  un.c = a.tile_c[t];
+  un.u = 1;
+  while (un.u < kTU && t + un.u < t1 && a.tile_c[t + un.u] == un.c) ++un.u;
+  t += un.u;
+  return true;
+}
+// this CTA's share [t0, t1) of batch b's tiles
+__device__ __forceinline__ void batch_range(const ApplyArgs& a, int b, int& c0, int& t0, int& t1) {
+  c0 = b * a.nb;
+  const int c1 = min(c0 + a.nb, a.n_src);
+  const int tb = __ldg(a.tile_ptr + c0), te = __ldg(a.tile_ptr + c1);
+  const int64_t total = te - tb;
+  t0 = tb + static_cast<int>((total * blockIdx.x) / gridDim.x);
+  t1 = tb + static_cast<int>((total * (blockIdx.x + 1)) / gridDim.x);
+}
+__device__ __forceinline__ void raise_when_all(int* cnt, int* ok, int target) {
+  const int prev = atomicAdd(cnt, 1);
+  if (prev == target - 1) {
+    __threadfence();
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(ok), "r"(1) : "memory");
+  }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kThreads, 1)
+k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMap tmY,
+           const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ApplyArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  const int b_chunk_bytes = a.cout * 128;
+  const int b_stride = (b_chunk_bytes + 1023) & ~1023;
+  uint8_t* smem_b = smem;
+  uint8_t* smem_a = smem_b + a.nb_slots * b_stride;
+  uint8_t* smem_y = smem_a + a.a_stages * kATileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_y + kYStages * kYStageBytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kMaxAStages;
+  uint64_t* b_full = a_empty + kMaxAStages;
+  uint64_t* b_empty = b_full + kMaxSlots;
+  uint64_t* tfull = b_empty + kMaxSlots;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* y_full = tempty + 2;
+  uint64_t* y_empty = y_full + kYStages;
+  uint64_t* yt_full = y_empty + kYStages;
+  uint64_t* yt_empty = yt_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yt_empty + 2);
+
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const unsigned long long tr0 = a.trace.rec ? gtime() : 0ull;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 8; ++i) prefetch_tmap(&tmH.m[i]);
+    prefetch_tmap(&tmY);
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmW);
+    for (int s = 0; s < a.a_stages; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int j = 0; j < a.nb_slots; ++j) {
+      mbar_init(&b_full[j], 1);
+      mbar_init(&b_empty[j], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);
+      mbar_init(&yt_full[s], 1);
+      mbar_init(&yt_empty[s], 4);
+    }
+    for (int s = 0; s < kYStages; ++s) {
+      mbar_init(&y_full[s], 1);
+      mbar_init(&y_empty[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_y = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ============================================================ contraction: TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      int prev_c = -1;
+      uint32_t ld = 0;
+      for (int b = 0; b < a.n_batches; ++b) {
+        int c0, t0, t1;
+        batch_range(a, b, c0, t0, t1);
+        if (t0 < t1) flag_wait(a.okY + b);               // Y of this batch is complete (and visible to TMA)
+        const int ring_row0 = (b % a.ring) * a.nb - c0;   // ring row of source c = ring_row0 + c
+        int t = t0;
+        Unit un;
+        while (next_unit(a, t1, t, un)) {
+          for (int p = 0; p < a.passes; ++p) {
+            const bool need = a.passes > 1 || un.c != prev_c;
+            for (int ti = 0; ti < un.u; ++ti) {
+              const int e0 = a.tile_e0[un.t + ti];
+              const int box = (a.tile_cnt[un.t + ti] + 15) >> 4;
+              const CUtensorMap* mh = &tmH.m[box - 1];
+              const uint32_t a_bytes = static_cast<uint32_t>(box) * 16u * 128u;
+              for (int s = 0; s < a.nb_slots; ++s) {
+                const int j = p * a.nb_slots + s;
+                if (need && ti == 0) {
+                  mbar_wait(&b_empty[s], (ld & 1u) ^ 1u);
+                  mbar_arrive_expect_tx(&b_full[s], b_chunk_bytes);
+                  tma_load_2d(smem_b + s * b_stride, &tmY, &b_full[s], j * 64, (ring_row0 + un.c) * a.cout, kEvictLast);
+                }
+                mbar_wait(&a_empty[stage], phase ^ 1u);
+                mbar_arrive_expect_tx(&a_full[stage], a_bytes);
+                tma_load_2d(smem_a + stage * kATileBytes, mh, &a_full[stage], 0, j * a.e_pad + e0, kEvictFirst);
+                if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
+              }
+            }
+            if (need) ++ld;
+          }
+          prev_c = un.c;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ============================================================ contraction: MMA issuer
+      const uint32_t idesc = idesc_f16(FMT, 128, static_cast<uint32_t>(a.cout));
+      int stage = 0;
+      uint32_t phase = 0;
+      int prev_c = -1;
+      uint32_t ld = 0;
+      int it = 0;
+      for (int b = 0; b < a.n_batches; ++b) {
+        int c0, t0, t1;
+        batch_range(a, b, c0, t0, t1);
+        int t = t0;
+        Unit un;
+        while (next_unit(a, t1, t, un)) {
+          const int as = it & 1;
+          mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1u);
+          fence_after_sync();
+          // B is re-loaded for every (unit, pass) when passes > 1, and across batches always (ring slot
+          // changes); within a batch with passes == 1 it stays while the source stays
+          const bool has_next = t < t1;
+          const bool next_same = has_next && a.tile_c[t] == un.c;
+          for (int p = 0; p < a.passes; ++p) {
+            const bool need = a.passes > 1 || un.c != prev_c;
+            const bool release = (p + 1 < a.passes) || a.passes > 1 || !next_same;
+            for (int ti = 0; ti < un.u; ++ti) {
+              const uint32_t d_tmem = tmem_base + (as * kTU + ti) * a.cout;
+              for (int s = 0; s < a.nb_slots; ++s) {
+                if (need && ti == 0) mbar_wait(&b_full[s], ld & 1u);
+                mbar_wait(&a_full[stage], phase);
+                fence_after_sync();
+                const uint64_t adesc = smem_desc_sw128(smem_u32(smem_a + stage * kATileBytes));
+                const uint64_t bdesc = smem_desc_sw128(smem_u32(smem_b + s * b_stride));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (p | s | k) != 0);
+                umma_commit(&a_empty[stage]);
+                if (release && ti == un.u - 1) umma_commit(&b_empty[s]);
+                if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
+              }
+            }
+            if (need) ++ld;
+          }
+          umma_commit(&tfull[as]);
+          prev_c = un.c;
+          ++it;
+        }
+        prev_c = -1;   // a new batch reads a different ring slot: never keep B across batches
+      }
+    }
+  } else if (warp < 6) {
+    // ================================================================ contraction: epilogue warps 2..5
+    const int quarter = warp % 4;
+    int it = 0;
+    for (int b = 0; b < a.n_batches; ++b) {
+      int c0, t0, t1;
+      batch_range(a, b, c0, t0, t1);
+      int t = t0;
+      Unit un;
+      while (next_unit(a, t1, t, un)) {
+        const int as = it & 1;
+        const int r = quarter * 32 + lane;
+        int d[kTU];
+        float sc[kTU];
+        bool ok[kTU];
+#pragma unroll
+        for (int ti = 0; ti < kTU; ++ti) {
+          ok[ti] = ti < un.u && r < a.tile_cnt[un.t + ti];
+          d[ti] = 0;
+          sc[ti] = 1.f;
+          if (ok[ti]) {
+            d[ti] = __ldg(a.dst_sorted + a.tile_e0[un.t + ti] + r);
+            if (a.inv_deg) sc[ti] = __ldg(a.inv_deg + d[ti]);
+          }
+        }
+        const float* cv = a.cvec + static_cast<int64_t>(un.c) * a.cout;
+        mbar_wait(&tfull[as], (it >> 1) & 1);
+        fence_after_sync();
+#pragma unroll
+        for (int ti = 0; ti < kTU; ++ti) {
+          if (ti < un.u) {
+            float* orow = a.out + static_cast<int64_t>(d[ti]) * a.cout;
+#pragma unroll 1
+            for (int cc = 0; cc < a.cout; cc += 16) {
+              uint32_t v[16];
+              tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * kTU + ti) * a.cout + cc, v);
+              tmem_ld_wait();
+              if (ok[ti]) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 cq = __ldg(reinterpret_cast<const float4*>(cv + cc) + q);
+                  red_add_v4(orow + cc + 4 * q, (__uint_as_float(v[4 * q + 0]) + cq.x) * sc[ti],
+                             (__uint_as_float(v[4 * q + 1]) + cq.y) * sc[ti],
+                             (__uint_as_float(v[4 * q + 2]) + cq.z) * sc[ti],
+                             (__uint_as_float(v[4 * q + 3]) + cq.w) * sc[ti]);
+                }
+              }
+            }
+          }
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[as]);
+        ++it;
+      }
+      // all MMAs of this CTA that read batch b's ring slot have completed (tfull of its last unit observed):
+      // one arrival per CTA; the last CTA frees the ring slot for the Y pipeline
+      if (warp == 2 && lane == 0) raise_when_all(a.cntC + b, a.okC + b, static_cast<int>(gridDim.x));
+    }
+  } else if (warp == 6) {
+    if (lane == 0) {
+      // ============================================================ Y GEMM: TMA producer
+      const int n_blocks = a.NY / kYBlockN;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int b = 0; b < a.n_batches; ++b) {
+        const int c0 = b * a.nb;
+        const int rows = min(a.nb, a.n_src - c0);
+        const int tiles = ((rows + 127) / 128) * n_blocks;
+        for (int i = static_cast<int>((blockIdx.x + 7u * b) % gridDim.x); i < tiles; i += gridDim.x) {
+          const int mb = i / n_blocks, nbk = i % n_blocks;
+          for (int kx = 0; kx < a.num_kx; ++kx) {
+            mbar_wait(&y_empty[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&y_full[stage], kYStageBytes);
+            uint8_t* st = smem_y + stage * kYStageBytes;
+            tma_load_2d(st, &tmX, &y_full[stage], kx * 64, c0 + mb * 128, kEvictLast);
+            tma_load_2d(st + kATileBytes, &tmW, &y_full[stage], kx * 64, nbk * kYBlockN, kEvictLast);
+            if (++stage == kYStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 7) {
+    if (lane == 0) {
+      // ============================================================ Y GEMM: MMA issuer
+      constexpr uint32_t idesc = idesc_f16(FMT, 128, kYBlockN);
+      const int n_blocks = a.NY / kYBlockN;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int b = 0; b < a.n_batches; ++b) {
+        const int c0 = b * a.nb;
+        const int rows = min(a.nb, a.n_src - c0);
+        const int tiles = ((rows + 127) / 128) * n_blocks;
+        for (int i = static_cast<int>((blockIdx.x + 7u * b) % gridDim.x); i < tiles; i += gridDim.x, ++it) {
+          const int ys = it & 1;
+          mbar_wait(&yt_empty[ys], ((it >> 1) & 1) ^ 1u);
+          fence_after_sync();
+          for (int kx = 0; kx < a.num_kx; ++kx) {
+            mbar_wait(&y_full[stage], phase);
+            fence_after_sync();
+            uint8_t* st = smem_y + stage * kYStageBytes;
+            const uint64_t adesc = smem_desc_sw128(smem_u32(st));
+            const uint64_t bdesc = smem_desc_sw128(smem_u32(st + kATileBytes));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_y + ys * kYBlockN, adesc + 2 * k, bdesc + 2 * k, idesc, (kx | k) != 0);
+            umma_commit(&y_empty[stage]);
+            if (kx == a.num_kx - 1) umma_commit(&yt_full[ys]);
+            if (++stage == kYStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else {
+    // ================================================================ Y GEMM: epilogue warps 8..11
+    const int quarter = warp % 4;
+    const int n_blocks = a.NY / kYBlockN;
+    int it = 0;
+    for (int b = 0; b < a.n_batches; ++b) {
+      const int c0 = b * a.nb;
+      const int rows = min(a.nb, a.n_src - c0);
+      const int tiles = ((rows + 127) / 128) * n_blocks;
+      if (b >= a.ring) {                         // the ring slot must have been consumed by every CTA
+        if (lane == 0) flag_wait(a.okC + (b - a.ring));
+        __syncwarp();
+      }
+      uint16_t* ybase = reinterpret_cast<uint16_t*>(a.Yring) + static_cast<int64_t>(b % a.ring) * a.nb * a.NY;
+      for (int i = static_cast<int>((blockIdx.x + 7u * b) % gridDim.x); i < tiles; i += gridDim.x, ++it) {
+        const int mb = i / n_blocks, nbk = i % n_blocks;
+        const int ys = it & 1;
+        mbar_wait(&yt_full[ys], (it >> 1) & 1);
+        fence_after_sync();
+        const int row = mb * 128 + quarter * 32 + lane;
+        const bool row_ok = row < rows;
+        uint16_t* yrow = ybase + static_cast<int64_t>(row) * a.NY + nbk * kYBlockN;
+        const uint32_t tb = tmem_y + (static_cast<uint32_t>(quarter * 32) << 16) + ys * kYBlockN;
+        uint32_t v[2][32];
+        tmem_ld32(tb, v[0]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < kYBlockN / 32; ++cc) {
+          if (cc + 1 < kYBlockN / 32) tmem_ld32(tb + (cc + 1) * 32, v[(cc + 1) & 1]);
+          if (row_ok) {
+            const uint32_t* vv = v[cc & 1];
+            uint32_t packed[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float f0 = __uint_as_float(vv[2 * j]), f1 = __uint_as_float(vv[2 * j + 1]);
+              if (FMT == 0) {
+                __half2 hh = __floats2half2_rn(f0, f1);
+                packed[j] = *reinterpret_cast<uint32_t*>(&hh);
+              } else {
+                __nv_bfloat162 hh = __floats2bfloat162_rn(f0, f1);
+                packed[j] = *reinterpret_cast<uint32_t*>(&hh);
+              }
+            }
+            st_global_v8(yrow + cc * 32, packed);
+            st_global_v8(yrow + cc * 32 + 16, packed + 8);
+          }
+          if (cc + 1 < kYBlockN / 32) tmem_ld_wait();
+        }
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&yt_empty[ys]);
+      }
+      // this warp's stores of batch b are out: 4 warps x grid arrivals complete the batch
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) raise_when_all(a.cntY + b, a.okY + b, 4 * static_cast<int>(gridDim.x));
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+  if (threadIdx.x == 0) trace_write(a.trace, 300u, tr0, tr0, a.trace.rec ? gtime() : 0ull);
+}
+
+struct ApplyShape {
+  int nb_slots, passes, a_stages, smem_bytes;
+};
+
+bool apply_shape(int cout, int Kp, ApplyShape* as) {
+  if (cout % 16 != 0 || cout < 16 || 2 * kTU * cout > 256 || Kp % 64 != 0) return false;
+  const int num_kc = Kp / 64;
+  const int b_stride = (cout * 128 + 1023) & ~1023;
+  const int bar_bytes = 1024;
+  const int budget = 227 * 1024 - bar_bytes - kYStages * kYStageBytes;
+  // fewest passes that leave >= 5 A stages (the h stream needs the bytes in flight), else >= 3
+  for (int min_stages = 5; min_stages >= 3; min_stages -= 2) {
+    for (int passes = 1; passes <= num_kc; ++passes) {
+      if (num_kc % passes) continue;
+      const int nb = num_kc / passes;
+      if (nb > kMaxSlots) continue;
+      if (passes > 1 && nb < 4) continue;   // too little time between a slot's release and its next use
+      int stages = (budget - nb * b_stride) / kATileBytes;
+      if (stages > kMaxAStages) stages = kMaxAStages;
+      if (stages >= min_stages) {
+        as->nb_slots = nb;
+        as->passes = passes;
+        as->a_stages = stages;
+        as->smem_bytes = nb * b_stride + stages * kATileBytes + kYStages * kYStageBytes + bar_bytes;
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+}  // namespace
+
+bool apply_fused_supported(const Weights* W) {
+  if (W->prec != PREC_F16 && W->prec != PREC_BF16) return false;
+  if ((W->cout * W->Kp) % kYBlockN != 0) return false;
+  ApplyShape as;
+  return apply_shape(W->cout, W->Kp, &as);
+}
+
+int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, const void* Xc, void* Yring, int nb,
+                    int ring, const float* cvec, int aggr_mean, float* out, int* flags, int flags_stride,
+                    cudaStream_t st) {
+  int s = tc_init();
+  if (s != NNCONV_OK) return s;
+  const int bf = prec == PREC_BF16;
+  ApplyShape as;
+  NNC_REQUIRE(apply_shape(W->cout, W->Kp, &as), NNCONV_ERR_UNSUPPORTED, "apply_tc: unsupported shape");
+  const int64_t e_pad = round_up64(P->E, 128);
+  const int NY = W->cout * W->Kp;
+  const int n_batches = ceil_div(P->n_src, nb);
+  NNC_REQUIRE(n_batches <= flags_stride, NNCONV_ERR_WORKSPACE, "apply_tc: too many source batches (%d)", n_batches);
+  HMaps tmH;
+  CUtensorMap tmY, tmX, tmW;
+  for (int i = 0; i < 8; ++i) {
+    s = make_tmap_2d_16b(&tmH.m[i], bf, h, static_cast<uint64_t>(W->Kp / 64) * e_pad, 64, 16 * (i + 1));
+    if (s != NNCONV_OK) return s;
+  }
+  s = make_tmap_2d_16b(&tmY, bf, Yring, static_cast<uint64_t>(ring) * nb * W->cout, static_cast<uint64_t>(W->Kp), W->cout);
+  if (s != NNCONV_OK) return s;
+  s = make_tmap_2d_16b(&tmX, bf, Xc, static_cast<uint64_t>(P->n_src), static_cast<uint64_t>(W->cin_p), 128);
+  if (s != NNCONV_OK) return s;
+  s = make_tmap_2d_16b(&tmW, bf, W->W3p, static_cast<uint64_t>(NY), static_cast<uint64_t>(W->cin_p), kYBlockN);
+  if (s != NNCONV_OK) return s;
+  ApplyArgs a;
+  a.tile_c = P->tile_c; a.tile_e0 = P->tile_e0; a.tile_cnt = P->tile_cnt; a.tile_ptr = P->tile_ptr;
+  a.dst_sorted = P->dst_sorted; a.inv_deg = aggr_mean ? P->inv_deg : nullptr; a.cvec = cvec; a.out = out;
+  a.n_src = P->n_src; a.nb = nb; a.n_batches = n_batches; a.ring = ring;
+  a.cout = W->cout; a.nb_slots = as.nb_slots; a.passes = as.passes; a.a_stages = as.a_stages;
+  a.e_pad = static_cast<int>(e_pad);
+  a.NY = NY; a.num_kx = W->cin_p / 64; a.Yring = Yring;
+  a.cntY = flags; a.cntC = flags + flags_stride; a.okY = flags + 2 * flags_stride; a.okC = flags + 3 * flags_stride;
+  {
+    TraceHandle th = trace_get();
+    a.trace = TraceBuf{th.rec, th.count, th.cap};
+  }
+  static int attr_set[2] = {0, 0};
+  if (!attr_set[bf]) {
+    if (bf) NNC_CHECK_CUDA(cudaFuncSetAttribute(k_apply_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    else NNC_CHECK_CUDA(cudaFuncSetAttribute(k_apply_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set[bf] = 1;
+  }
+  // every CTA must be resident (the flags couple all CTAs): exactly one CTA per SM, never more than #SMs
+  const int grid = tc_num_sms();
+  if (bf) k_apply_tc<1><<<grid, kThreads, as.smem_bytes, st>>>(tmH, tmY, tmX, tmW, a);
+  else k_apply_tc<0><<<grid, kThreads, as.smem_bytes, st>>>(tmH, tmY, tmX, tmW, a);
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
+}
+
+}  // namespace nnc

@@ -54,7 +54,7 @@ struct Carver {
 constexpr int kTileEdges = 128;
 
 // Optional per-kernel-class timing with CUDA events (bench.py roofline numbers); off by default.
-enum ProfKind : int { PK_LAYER1 = 0, PK_HIDDEN_GEMM = 1, PK_NODE_PREP = 2, PK_Y_GEMM = 3, PK_CONV = 4, PK_COUNT = 5 };
+enum ProfKind : int { PK_LAYER1 = 0, PK_HIDDEN_GEMM = 1, PK_NODE_PREP = 2, PK_Y_GEMM = 3, PK_CONV = 4, PK_APPLY_FUSED = 5, PK_COUNT = 6 };
 bool prof_enabled();
 void prof_mark(int kind, cudaStream_t st, bool begin);
 struct ProfScope {

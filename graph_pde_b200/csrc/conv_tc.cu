@@ -304,7 +304,7 @@ bool conv_shape(int cout, int Kp, ConvShape* cs) {
   const int bar_bytes = 512;
   const int acc_cols = 2 * kTU * cout;
   if (acc_cols > 512) return false;
-  static const bool one_per_sm = getenv("NNCONV_CONV_ONE_PER_SM") != nullptr;   // measurement knob
+  const bool one_per_sm = getenv("NNCONV_CONV_ONE_PER_SM") != nullptr;   // measurement knob
   for (int two = one_per_sm ? 0 : 1; two >= 0; --two) {
     if (two && acc_cols > 256) continue;
     const int budget = two ? kSmemTwoPerSm : 227 * 1024;

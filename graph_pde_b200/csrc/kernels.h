@@ -55,6 +55,12 @@ int launch_conv_tc(int prec, const Plan* P, const void* h, int Kp, const void* Y
                    int tile_begin, int tile_end, int c0, const float* cvec, int aggr_mean, float* out,
                    cudaStream_t st, const PipeFlags* pf = nullptr);
 
+// ---- apply_tc.cu: ONE persistent kernel per application (Y GEMM + contraction pipelines in every CTA)
+bool apply_fused_supported(const Weights* W);
+int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, const void* Xc, void* Yring, int nb,
+                    int ring, const float* cvec, int aggr_mean, float* out, int* flags, int flags_stride,
+                    cudaStream_t st);
+
 bool tc_shapes_supported(const Weights* W);
 int tc_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes; idempotent
 

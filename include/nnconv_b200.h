@@ -109,9 +109,10 @@ int nnconv_apply(const nnconv_plan_t* plan, const nnconv_weights_t* w, const voi
 
 /* ---- measurement hook (bench.py): while enabled, every kernel launch is bracketed by CUDA events on its
  * stream; profile_end synchronises the device and returns summed milliseconds / launch counts per kernel
- * class: 0 first MLP layer, 1 hidden-layer GEMM, 2 per-node prologue, 3 per-source Y GEMM,
- * 4 contraction+scatter.  Not thread safe; not for production use. */
-#define NNCONV_PROFILE_KINDS 5
+ * class: 0 first MLP layer, 1 hidden-layer GEMM, 2 per-node prologue, 3 per-source Y GEMM (unfused path),
+ * 4 contraction+scatter (unfused path), 5 fused persistent application kernel (Y GEMM + contraction).
+ * Not thread safe; not for production use. */
+#define NNCONV_PROFILE_KINDS 6
 int nnconv_profile_begin(void);
 int nnconv_profile_end(double* ms_by_kind, int64_t* launches_by_kind, int n_kinds);
 

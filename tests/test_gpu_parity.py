@@ -165,3 +165,30 @@ def test_properties_at_config2_size(dev):
     assert lin_err < 2e-3
     deg = torch.zeros(s * s).index_add_(0, ei[1], torch.ones(ei.size(1))).clamp(min=1).to(dev)
     assert rel_err(o_mean, o_add / deg[:, None]) < 1e-5
+
+
+@pytest.mark.parametrize('knob', ['NNCONV_NO_FUSE', 'NNCONV_NO_PIPE+NNCONV_NO_FUSE', 'NNCONV_RING=2', 'small_ring'])
+def test_alternative_schedules_give_the_same_answer(dev, knob, monkeypatch):
+    """The fused persistent kernel (default), the per-batch PDL-pipelined kernels (NNCONV_NO_FUSE) and the
+    plain stream-ordered kernels (NNCONV_NO_PIPE) must agree; a tiny Y ring forces many batches through the
+    flag protocol."""
+    from graph_pde_b200 import nn_conv
+    for kv in knob.split('+'):
+        if kv == 'small_ring':
+            monkeypatch.setattr(nn_conv, '_Y_BYTES', 64 * 128 * 2 * 64 * 3)     # ~3 sources per ring slot... many batches
+        elif '=' in kv:
+            k, v = kv.split('=')
+            monkeypatch.setenv(k, v)
+        else:
+            monkeypatch.setenv(kv, '1')
+    g = np.load(os.path.join(GOLDEN, 'g3_checkpoint_grain_new.npz'))
+    st = {k[2:]: g[k] for k in g.files if k.startswith('w/')}
+    ws = [st['conv1.nn.layers.%d.weight' % i] for i in (0, 2, 4)]
+    bs = [st['conv1.nn.layers.%d.bias' % i] for i in (0, 2, 4)]
+    conv = make_conv(_conv_cls(), ws, bs, st['conv1.root'], st['conv1.bias'], 'mean', 64, 64, 'f16', dev)
+    ei, ea = ei64(g['edge_index']).to(dev), t(g['edge_attr']).to(dev)
+    x = t(g['x0']).to(dev)
+    with torch.no_grad():
+        for k in range(6):
+            x = torch.relu(conv(x, ei, ea))
+            assert rel_err(x, t(g['x_after'][k])) < TOL['f16'], (knob, k)
