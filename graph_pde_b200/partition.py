@@ -1,0 +1,116 @@
+"""Multi-GPU decomposition of the NNConv path; the reference itself is single-GPU.
+
+Two ways the path shards, both one process per GPU over torch.distributed (NCCL on the B200 box, gloo in
+the CPU tests):
+
+1. **Batch sharding** (BASELINE config 3): graphs of a training / inference batch are independent connected
+   components, so rank r owns graphs g with g % world == r.  Forward has NO data-path collective; training
+   adds one all-reduce of parameter gradients per step.  ``shard_indices`` + ``allreduce_gradients``.
+
+2. **Node-range cuts of one big mesh** (config 3 alt. / 5): the square grid is row-major (node = iy*s + ix,
+   graph-neural-operator/utilities.py:248), so contiguous node ranges are horizontal strips.  A ball of
+   radius r reaches R = floor(r*(s-1)) grid rows, hence a rank needs R halo rows above and below its strip;
+   edges are assigned to the owner of their DESTINATION so the scatter stays local, and ONE halo exchange
+   (all-gather of every rank's 2R boundary rows) precedes each of the T conv applications.
+   ``StripPartition`` builds the local sub-graph with the reference's edge order, ``halo_exchange`` moves the
+   boundary rows.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import graphs
+
+
+def shard_indices(n_items, rank, world):
+    """Round-robin ownership of independent graphs: item g belongs to rank g % world."""
+    return list(range(rank, n_items, world))
+
+
+def allreduce_gradients(module, group=None):
+    """Sum-reduce parameter gradients across ranks (the reference's losses are sums over the batch,
+    UAI1_full_resolution.py:265, so no rescale).  One flat all-reduce: ~21 MB for KernelNN(w=64, kw=1024)."""
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+
+
+class StripPartition(object):
+    """Horizontal-strip partition of the s x s ball graph for one rank.
+
+    Local node numbering: [halo_above | owned | halo_below] (global order preserved), so local index =
+    global index - first_local_global.  ``edge_index`` (local numbering, int64 [2, E_loc]) holds every edge
+    whose destination is owned, in the reference's source-major order; ``edge_ids`` are not needed because
+    edge attributes are recomputed from positions / theta exactly like the reference does per sample.
+    """
+
+    def __init__(self, s, r, rank, world, device='cpu', ties_in=True):
+        self.s, self.r, self.rank, self.world = s, r, rank, world
+        self.R = int(math.floor(r * (s - 1) + 1e-9))
+        rows = [(s * k) // world for k in range(world + 1)]          # row ranges per rank
+        self.row_lo, self.row_hi = rows[rank], rows[rank + 1]
+        self.all_rows = rows
+        if min(b - a for a, b in zip(rows[:-1], rows[1:])) < self.R:
+            raise ValueError('strips thinner than the ball radius need multi-hop halos (not built)')
+        self.halo_lo = max(0, self.row_lo - self.R)
+        self.halo_hi = min(s, self.row_hi + self.R)
+        self.first = self.halo_lo * s                                  # global id of local node 0
+        self.n_local = (self.halo_hi - self.halo_lo) * s
+        self.own_lo = (self.row_lo - self.halo_lo) * s                # local range of owned nodes
+        self.own_hi = self.own_lo + (self.row_hi - self.row_lo) * s
+        ei = graphs.ball_connectivity(s, r, device, ties_in, nodes=(self.halo_lo * s, self.halo_hi * s))
+        keep = (ei[1] >= self.row_lo * s) & (ei[1] < self.row_hi * s)  # destination owned
+        self.edge_index_global = ei[:, keep]
+        self.edge_index = self.edge_index_global - self.first
+
+    def local_slice(self, x_global):
+        return x_global[self.first:self.first + self.n_local]
+
+    def boundary_rows(self, x_local):
+        """The 2R owned grid rows (top R, bottom R) other ranks may need: [2R*s, C]."""
+        s, R = self.s, self.R
+        top = x_local[self.own_lo:self.own_lo + R * s]
+        bot = x_local[self.own_hi - R * s:self.own_hi]
+        return torch.cat([top, bot], dim=0)
+
+
+def halo_exchange(x_local, part, group=None):
+    """Refresh the halo rows of x_local in place from the neighbours' boundary rows.
+    One all-gather of [2R*s, C] per rank (740 KB per side at 241^2, r=0.05, C=64 fp32)."""
+    s, R = part.s, part.R
+    send = part.boundary_rows(x_local).contiguous()
+    if part.world == 1:
+        return x_local
+    bufs = [torch.empty_like(send) for _ in range(part.world)]
+    dist.all_gather(bufs, send, group=group)
+    # halo above = bottom R rows of rank-1 ; halo below = top R rows of rank+1
+    n_above = (part.row_lo - part.halo_lo) * s
+    if n_above > 0:
+        x_local[:n_above] = bufs[part.rank - 1][R * s:][-n_above:]
+    n_below = (part.halo_hi - part.row_hi) * s
+    if n_below > 0:
+        x_local[part.own_hi:part.own_hi + n_below] = bufs[part.rank + 1][:R * s][:n_below]
+    return x_local
+
+
+def partitioned_conv_stack(conv_fn, x_local, part, edge_attr_local, depth, relu_last=True, group=None):
+    """T applications of a shared conv on one rank's strip.  ``conv_fn(x, edge_index, edge_attr) -> [n_local,
+    C]`` computes rows for every local node but only OWNED rows are meaningful (edges end in owned nodes);
+    halo rows are overwritten by the exchange before the next application."""
+    x = x_local
+    for k in range(depth):
+        out = conv_fn(x, part.edge_index, edge_attr_local)
+        if relu_last or k != depth - 1:
+            out = torch.relu(out)
+        x = out
+        if k != depth - 1:
+            x = halo_exchange(x, part, group)
+    return x[part.own_lo:part.own_hi]

@@ -192,3 +192,27 @@ def test_alternative_schedules_give_the_same_answer(dev, knob, monkeypatch):
         for k in range(6):
             x = torch.relu(conv(x, ei, ea))
             assert rel_err(x, t(g['x_after'][k])) < TOL['f16'], (knob, k)
+
+
+def test_block_diagonal_batch_equals_per_graph(dev):
+    """PyG Batch collation (block-diagonal edge_index, node offset): batched conv == per-graph conv
+    (UAI3_resolution.py:191 uses batch 10); also the drop-in DataLoader's collation rule."""
+    gen = torch.Generator().manual_seed(21)
+    w = 64
+    torch.manual_seed(5)
+    mlp = DenseNetLike([6, 64, w * w])
+    lin = [m for m in mlp.layers if isinstance(m, torch.nn.Linear)]
+    ws, bs = [l.weight.detach() for l in lin], [l.bias.detach() for l in lin]
+    conv = make_conv(_conv_cls(), ws, bs, torch.randn(w, w) * 0.1, torch.randn(w) * 0.1, 'mean', w, w, 'f16', dev)
+    graphs_ = []
+    for n, e in ((50, 400), (80, 900), (33, 100)):
+        ei = torch.stack([torch.randint(0, n, (e,), generator=gen), torch.randint(0, n, (e,), generator=gen)])
+        graphs_.append((torch.randn(n, w, generator=gen), ei, torch.randn(e, 6, generator=gen)))
+    with torch.no_grad():
+        singles = [conv(x.to(dev), ei.to(dev), ea.to(dev)) for x, ei, ea in graphs_]
+        off = np.cumsum([0] + [g[0].size(0) for g in graphs_])
+        xb = torch.cat([g[0] for g in graphs_]).to(dev)
+        eib = torch.cat([g[1] + int(o) for g, o in zip(graphs_, off)], dim=1).to(dev)
+        eab = torch.cat([g[2] for g in graphs_]).to(dev)
+        outb = conv(xb, eib, eab)
+    assert rel_err(outb, torch.cat(singles)) < 5e-4

@@ -111,3 +111,25 @@ def test_graph_builder_matches_oracle_and_sklearn_golden():
     sel = (full[0] >= 100) & (full[0] < 140)
     assert torch.equal(part, full[:, sel])
     assert full.size(1) == 25673                                # ties-in rule
+
+
+def test_dropin_modules_resolve_like_the_reference_imports(monkeypatch):
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.syspath_prepend(os.path.join(root, 'dropin'))
+    for m in ('nn_conv', 'torch_geometric', 'torch_geometric.nn', 'torch_geometric.data'):
+        sys.modules.pop(m, None)
+    nn_conv_mod = importlib.import_module('nn_conv')
+    tg_nn = importlib.import_module('torch_geometric.nn')
+    tg_data = importlib.import_module('torch_geometric.data')
+    conv = nn_conv_mod.NNConv_old(8, 8, DenseNet([6, 16, 64], torch.nn.ReLU), aggr='mean')
+    assert type(conv).__module__ == 'nn_conv' and repr(conv) == 'NNConv_old(8, 8)'
+    assert issubclass(tg_nn.NNConv, NNConv_old)
+    # block-diagonal batching rule (PyG Batch): 'index' keys are offset by the node count
+    a = tg_data.Data(x=torch.zeros(3, 2), edge_index=torch.tensor([[0, 1], [1, 2]]), edge_attr=torch.zeros(2, 6))
+    b = tg_data.Data(x=torch.ones(2, 2), edge_index=torch.tensor([[0], [1]]), edge_attr=torch.ones(1, 6))
+    batch = next(iter(tg_data.DataLoader([a, b], batch_size=2)))
+    assert batch.x.shape == (5, 2) and batch.edge_index.tolist() == [[0, 1, 3], [1, 2, 4]]
+    for m in ('nn_conv', 'torch_geometric', 'torch_geometric.nn', 'torch_geometric.data'):
+        sys.modules.pop(m, None)
