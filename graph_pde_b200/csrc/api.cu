@@ -152,11 +152,17 @@ static int max_hidden_kp(const Weights* W) {
   return m;
 }
 
+static bool ef_fuse12(const Weights* W) {
+  // first two layers in one kernel (mlp_fused_tc.cu): needs the tensor-core first layer and a hidden layer
+  return W->W1aug != nullptr && W->n_layers >= 3 && getenv("NNCONV_NO_FUSE12") == nullptr;
+}
+
 static size_t ef_row_bytes(const Weights* W) {
   // per edge row of workspace: A1 (64 x 16-bit, tensor-core first layer) + ping/pong hidden activations
   size_t row = 0;
   if (W->W1aug) row += 128;
-  if (W->n_layers > 2) row += 2 * static_cast<size_t>(max_hidden_kp(W)) * W->esize;
+  const bool fuse = ef_fuse12(W);
+  if (W->n_layers > (fuse ? 3 : 2)) row += 2 * static_cast<size_t>(max_hidden_kp(W)) * W->esize;
   return row;
 }
 
@@ -198,6 +204,7 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
   NNC_REQUIRE(ws != nullptr && ws_bytes >= 128 * rowb + 4096, NNCONV_ERR_WORKSPACE, "edge_features: workspace too small");
   const int64_t rows = static_cast<int64_t>((ws_bytes - 4096) / rowb) / 128 * 128;
   const size_t hid = static_cast<size_t>(max_hidden_kp(W)) * W->esize;
+  const bool fuse12 = ef_fuse12(W);
   char* a1 = static_cast<char*>(ws);
   char* bufA = a1 + (W->W1aug ? round_up64(rows * 128, 1024) : 0);
   char* bufB = bufA + round_up64(static_cast<int64_t>(rows * hid), 1024);
@@ -206,7 +213,23 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
     void* h_rows = hpad > 0 ? h : static_cast<void*>(static_cast<char*>(h) + static_cast<size_t>(e0) * W->Kp * W->esize);
     const int64_t h_pad_l1 = nl == 2 ? hpad : 0;     // first layer writes h directly only for 2-layer MLPs
     void* dst1 = nl == 2 ? h_rows : static_cast<void*>(bufA);
-    {
+    int first_hidden = 2;
+    if (fuse12) {   // layers 1+2 fused: A1 -> (h1 on chip) -> h2
+      {
+        ProfScope ps(PK_LAYER1, st);
+        s = launch_build_a1(W->prec, edge_attr, P->perm, e0, n, W->dims[0], a1, st);
+      }
+      if (s) return s;
+      const bool last2 = nl == 3;
+      {
+        ProfScope ps(PK_HIDDEN_GEMM, st);
+        s = launch_mlp12_tc(W->prec, a1, n, W->dims[0], W->W1aug, W->kp[1], W->Wh[2], W->kp[2], W->bh[2],
+                            last2 ? h_rows : static_cast<void*>(bufA), W->kp[2], last2 ? hpad : 0, e0, st);
+      }
+      if (s) return s;
+      if (launches) *launches += 2;
+      first_hidden = 3;
+    } else {
       ProfScope ps(PK_LAYER1, st);
       if (W->W1aug) {
         s = launch_build_a1(W->prec, edge_attr, P->perm, e0, n, W->dims[0], a1, st);
@@ -220,10 +243,10 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
       }
     }
     if (s) return s;
-    if (launches) ++*launches;
+    if (launches && !fuse12) ++*launches;
     char* cur = bufA;
     char* nxt = bufB;
-    for (int l = 2; l <= nl - 1; ++l) {
+    for (int l = first_hidden; l <= nl - 1; ++l) {
       const bool last = l == nl - 1;
       void* dst = last ? h_rows : static_cast<void*>(nxt);
       ProfScope ps(PK_HIDDEN_GEMM, st);
@@ -330,7 +353,7 @@ int apply(const Plan* P, const Weights* W, const void* h, const float* x, const 
   // the Y GEMM pipeline and the contraction pipeline concurrently over a ring of L2-resident Y batches.
   const bool no_fuse_env = getenv("NNCONV_NO_FUSE") != nullptr;      // measurement / debugging knob
   if (!no_fuse_env && apply_fused_supported(W)) {
-    int ring = 4;
+    int ring = 2;   // measured (r1e): batch granularity matters (each batch boundary costs ~8 us), ring depth does not
     if (const char* e = getenv("NNCONV_RING")) { int v = atoi(e); if (v >= 2 && v <= 8) ring = v; }
     if (nodes_cap < ring) ring = nodes_cap >= 2 ? static_cast<int>(nodes_cap) : 1;
     int64_t nb = nodes_cap / ring;

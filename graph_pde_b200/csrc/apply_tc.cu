@@ -58,6 +58,7 @@ struct ApplyArgs {
   int* okY;
   int* cntC;
   int* okC;
+  unsigned long long y_store_policy;   // L2 eviction-priority hint of the Y ring stores
   TraceBuf trace;
 };
 
@@ -163,10 +164,14 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
       uint32_t phase = 0;
       int prev_c = -1;
       uint32_t ld = 0;
+      int nc0 = 0, nt0 = 0, nt1 = 0;
+      batch_range(a, 0, nc0, nt0, nt1);
       for (int b = 0; b < a.n_batches; ++b) {
-        int c0, t0, t1;
-        batch_range(a, b, c0, t0, t1);
+        const int c0 = nc0, t0 = nt0, t1 = nt1;
+        if (b + 1 < a.n_batches) batch_range(a, b + 1, nc0, nt0, nt1);   // loads overlap this batch's stream
+        const unsigned long long tw0 = a.trace.rec ? gtime() : 0ull;
         if (t0 < t1) flag_wait(a.okY + b);               // Y of this batch is complete (and visible to TMA)
+        if (a.trace.rec && (blockIdx.x % 37) == 0) trace_write(a.trace, 301u | (static_cast<unsigned>(b) << 12), tw0, gtime(), 0ull);
         const int ring_row0 = (b % a.ring) * a.nb - c0;   // ring row of source c = ring_row0 + c
         int t = t0;
         Unit un;
@@ -206,9 +211,11 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
       int prev_c = -1;
       uint32_t ld = 0;
       int it = 0;
+      int nc0 = 0, nt0 = 0, nt1 = 0;
+      batch_range(a, 0, nc0, nt0, nt1);
       for (int b = 0; b < a.n_batches; ++b) {
-        int c0, t0, t1;
-        batch_range(a, b, c0, t0, t1);
+        const int t0 = nt0, t1 = nt1;
+        if (b + 1 < a.n_batches) batch_range(a, b + 1, nc0, nt0, nt1);   // prefetch: off the critical path
         int t = t0;
         Unit un;
         while (next_unit(a, t1, t, un)) {
@@ -250,9 +257,11 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
     // ================================================================ contraction: epilogue warps 2..5
     const int quarter = warp % 4;
     int it = 0;
+    int nc0 = 0, nt0 = 0, nt1 = 0;
+    batch_range(a, 0, nc0, nt0, nt1);
     for (int b = 0; b < a.n_batches; ++b) {
-      int c0, t0, t1;
-      batch_range(a, b, c0, t0, t1);
+      const int t0 = nt0, t1 = nt1;
+      if (b + 1 < a.n_batches) batch_range(a, b + 1, nc0, nt0, nt1);
       int t = t0;
       Unit un;
       while (next_unit(a, t1, t, un)) {
@@ -368,10 +377,12 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
       const int c0 = b * a.nb;
       const int rows = min(a.nb, a.n_src - c0);
       const int tiles = ((rows + 127) / 128) * n_blocks;
+      const unsigned long long ty0 = a.trace.rec ? gtime() : 0ull;
       if (b >= a.ring) {                         // the ring slot must have been consumed by every CTA
         if (lane == 0) flag_wait(a.okC + (b - a.ring));
         __syncwarp();
       }
+      const unsigned long long ty1 = a.trace.rec ? gtime() : 0ull;
       uint16_t* ybase = reinterpret_cast<uint16_t*>(a.Yring) + static_cast<int64_t>(b % a.ring) * a.nb * a.NY;
       for (int i = static_cast<int>((blockIdx.x + 7u * b) % gridDim.x); i < tiles; i += gridDim.x, ++it) {
         const int mb = i / n_blocks, nbk = i % n_blocks;
@@ -402,8 +413,8 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
                 packed[j] = *reinterpret_cast<uint32_t*>(&hh);
               }
             }
-            st_global_v8(yrow + cc * 32, packed);
-            st_global_v8(yrow + cc * 32 + 16, packed + 8);
+            st_global_v8_hint(yrow + cc * 32, packed, a.y_store_policy);
+            st_global_v8_hint(yrow + cc * 32 + 16, packed + 8, a.y_store_policy);
           }
           if (cc + 1 < kYBlockN / 32) tmem_ld_wait();
         }
@@ -415,6 +426,8 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
       __threadfence();
       __syncwarp();
       if (lane == 0) raise_when_all(a.cntY + b, a.okY + b, 4 * static_cast<int>(gridDim.x));
+      if (a.trace.rec && warp == 8 && lane == 0 && (blockIdx.x % 37) == 0)
+        trace_write(a.trace, 302u | (static_cast<unsigned>(b) << 12), ty0, ty1, gtime());
     }
   }
   fence_before_sync();
@@ -497,6 +510,8 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
   a.cout = W->cout; a.nb_slots = as.nb_slots; a.passes = as.passes; a.a_stages = as.a_stages;
   a.e_pad = static_cast<int>(e_pad);
   a.NY = NY; a.num_kx = W->cin_p / 64; a.Yring = Yring;
+  a.y_store_policy = kEvictNormal;
+  if (const char* e = getenv("NNCONV_Y_STORE_POLICY")) a.y_store_policy = atoi(e) == 1 ? kEvictLast : atoi(e) == 2 ? kEvictFirst : kEvictNormal;
   a.cntY = flags; a.cntC = flags + flags_stride; a.okY = flags + 2 * flags_stride; a.okC = flags + 3 * flags_stride;
   {
     TraceHandle th = trace_get();

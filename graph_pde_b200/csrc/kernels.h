@@ -55,6 +55,11 @@ int launch_conv_tc(int prec, const Plan* P, const void* h, int Kp, const void* Y
                    int tile_begin, int tile_end, int c0, const float* cvec, int aggr_mean, float* out,
                    cudaStream_t st, const PipeFlags* pf = nullptr);
 
+// ---- mlp_fused_tc.cu: first two MLP layers in one kernel (h1 never leaves the SM)
+int launch_mlp12_tc(int prec, const void* A1, int64_t rows, int k_in, const void* W1aug, int K1p, const void* W2,
+                    int N, const float* bias2, void* C, int64_t ldc, int64_t chunk_rows_pad, int64_t c_row0,
+                    cudaStream_t st);
+
 // ---- apply_tc.cu: ONE persistent kernel per application (Y GEMM + contraction pipelines in every CTA)
 bool apply_fused_supported(const Weights* W);
 int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, const void* Xc, void* Yring, int nb,

@@ -161,6 +161,13 @@ __device__ __forceinline__ void st_global_v8(void* addr, const uint32_t* v) {
                : "memory");
 }
 
+// same with an L2 eviction-priority hint (Y ring: keep resident against the evict-first h stream)
+__device__ __forceinline__ void st_global_v8_hint(void* addr, const uint32_t* v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(addr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "l"(policy)
+               : "memory");
+}
+
 // ---------------------------------------------------------------- cross-kernel pipelining (PDL + flags)
 // Kernels of one NNConv application are launched with programmatic stream serialization: a kernel may
 // start as soon as every CTA of its predecessor has executed launch_dependents, i.e. CTAs of kernel k+1
@@ -179,7 +186,10 @@ __device__ __forceinline__ void flag_wait(const int* ok) {
 #pragma unroll 1
   for (uint32_t i = 0; i < (1u << 26); ++i) {
     if (ld_acquire(ok) != 0) {
-      asm volatile("fence.proxy.async;" ::: "memory");
+      // order the acquire (generic proxy) before the TMA reads (async proxy) of GLOBAL memory only: the
+      // unqualified fence also covers shared memory and drained the producer's in-flight TMA loads at every
+      // batch boundary (~8 us per batch, profiles/r1e_trace_fused_flags.md)
+      asm volatile("fence.proxy.async.global;" ::: "memory");
       return;
     }
     __nanosleep(64);
