@@ -153,8 +153,12 @@ static int max_hidden_kp(const Weights* W) {
 }
 
 static bool ef_fuse12(const Weights* W) {
-  // first two layers in one kernel (mlp_fused_tc.cu): needs the tensor-core first layer and a hidden layer
-  return W->W1aug != nullptr && W->n_layers >= 3 && getenv("NNCONV_NO_FUSE12") == nullptr;
+  // first two layers in one kernel (mlp_fused_tc.cu).  EXPERIMENTAL, off by default (NNCONV_FUSE12=1): every
+  // variant measured this round (profiles/r1e_*) was slower than the two separate GEMMs -- routing the fp32
+  // first-layer accumulator through TMEM costs a 32 KB tcgen05.ld per 64-column block, about the whole
+  // 576-cycle budget of that block at the measured TMEM read rate.
+  const char* e = getenv("NNCONV_FUSE12");
+  return W->W1aug != nullptr && W->n_layers >= 3 && e != nullptr && atoi(e) > 0;
 }
 
 static size_t ef_row_bytes(const Weights* W) {
@@ -280,7 +284,7 @@ static ApplyLayout layout_apply(const Plan* P, const Weights* W) {
   const size_t S = P->n_src > 0 ? P->n_src : 1;
   L.off_Xc = c.off; c.take<char>((S + 128) * W->cin_p * W->esize);
   L.off_cvec = c.off; c.take<float>(S * W->cout);
-  L.off_flags = c.off; c.take<int>(4 * kMaxPipeBatches);
+  L.off_flags = c.off; c.take<int>(5 * kMaxPipeBatches);
   L.off_Y = c.off;
   L.fixed_bytes = c.off;
   L.per_node = static_cast<size_t>(W->cout) * W->Kp * W->esize;
@@ -353,7 +357,7 @@ int apply(const Plan* P, const Weights* W, const void* h, const float* x, const 
   // the Y GEMM pipeline and the contraction pipeline concurrently over a ring of L2-resident Y batches.
   const bool no_fuse_env = getenv("NNCONV_NO_FUSE") != nullptr;      // measurement / debugging knob
   if (!no_fuse_env && apply_fused_supported(W)) {
-    int ring = 2;   // measured (r1e): batch granularity matters (each batch boundary costs ~8 us), ring depth does not
+    int ring = 3;   // measured (run22): with dynamic unit scheduling 3 x 128 sources (48 MB at out=64, Kp=1024) is best
     if (const char* e = getenv("NNCONV_RING")) { int v = atoi(e); if (v >= 2 && v <= 8) ring = v; }
     if (nodes_cap < ring) ring = nodes_cap >= 2 ? static_cast<int>(nodes_cap) : 1;
     int64_t nb = nodes_cap / ring;
@@ -361,7 +365,7 @@ int apply(const Plan* P, const Weights* W, const void* h, const float* x, const 
     if (nb > P->n_src) nb = P->n_src;
     if (ceil_div64(P->n_src, nb) <= kMaxPipeBatches && ring >= 2) {
       int* flags = reinterpret_cast<int*>(base + L.off_flags);
-      NNC_CHECK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 4 * kMaxPipeBatches, st));
+      NNC_CHECK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 5 * kMaxPipeBatches, st));
       {
         ProfScope ps(PK_APPLY_FUSED, st);
         s = launch_apply_tc(W->prec, P, W, h, Xc, Y, static_cast<int>(nb), ring, cvec, aggr_mean, out, flags,

@@ -37,6 +37,7 @@ constexpr int kYBlockN = 128;
 constexpr int kYStageBytes = kATileBytes + kYBlockN * 64 * 2;   // Xc tile + W3p tile
 constexpr int kYStages = 2;
 constexpr int kThreads = 384;
+constexpr int kQueue = 8;                  // unit queue between the scheduler and the MMA / epilogue warps
 
 struct ApplyArgs {
   // plan
@@ -44,6 +45,9 @@ struct ApplyArgs {
   const int* tile_e0;
   const int* tile_cnt;
   const int* tile_ptr;    // device [S+1]
+  const int* unit_ptr;    // device [S+1]
+  const int* unit_t;      // [U]
+  const int* unit_u;      // [U]
   const int* dst_sorted;
   const float* inv_deg;   // nullptr -> aggr = add
   const float* cvec;      // [S, cout]
@@ -58,6 +62,7 @@ struct ApplyArgs {
   int* okY;
   int* cntC;
   int* okC;
+  int* cntU;              // units handed out so far (one counter per application)
   unsigned long long y_store_policy;   // L2 eviction-priority hint of the Y ring stores
   TraceBuf trace;
 };
@@ -66,27 +71,6 @@ struct HMaps {
   CUtensorMap m[8];
 };
 
-struct Unit {
-  int t, u, c;
-};
-__device__ __forceinline__ bool next_unit(const ApplyArgs& a, int t1, int& t, Unit& un) {
-  if (t >= t1) return false;
-  un.t = t;
-  un.c = a.tile_c[t];
-  un.u = 1;
-  while (un.u < kTU && t + un.u < t1 && a.tile_c[t + un.u] == un.c) ++un.u;
-  t += un.u;
-  return true;
-}
-// this CTA's share [t0, t1) of batch b's tiles
-__device__ __forceinline__ void batch_range(const ApplyArgs& a, int b, int& c0, int& t0, int& t1) {
-  c0 = b * a.nb;
-  const int c1 = min(c0 + a.nb, a.n_src);
-  const int tb = __ldg(a.tile_ptr + c0), te = __ldg(a.tile_ptr + c1);
-  const int64_t total = te - tb;
-  t0 = tb + static_cast<int>((total * blockIdx.x) / gridDim.x);
-  t1 = tb + static_cast<int>((total * (blockIdx.x + 1)) / gridDim.x);
-}
 __device__ __forceinline__ void raise_when_all(int* cnt, int* ok, int target) {
   const int prev = atomicAdd(cnt, 1);
   if (prev == target - 1) {
@@ -117,7 +101,10 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
   uint64_t* y_empty = y_full + kYStages;
   uint64_t* yt_full = y_empty + kYStages;
   uint64_t* yt_empty = yt_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(yt_empty + 2);
+  uint64_t* q_full = yt_empty + 2;       // [kQueue] 1 arrival (scheduler)
+  uint64_t* q_empty = q_full + kQueue;   // [kQueue] 5 arrivals (MMA issuer + 4 epilogue warps)
+  int4* q_ent = reinterpret_cast<int4*>(q_empty + kQueue);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ent + kQueue);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const unsigned long long tr0 = a.trace.rec ? gtime() : 0ull;
@@ -145,6 +132,10 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
       mbar_init(&y_full[s], 1);
       mbar_init(&y_empty[s], 1);
     }
+    for (int s = 0; s < kQueue; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 5);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -157,50 +148,69 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_y = tmem_base + 256;
 
+  // ---- contraction work distribution: units (<= 2 tiles of one source) of batch b are handed out
+  // dynamically (atomic counter per batch) to whichever CTA is ready.  With a static equal split the period of
+  // every batch was set by its slowest CTA and fast CTAs idled 17-29 % (profiles/r1e_trace_fused_flags.md).
+  // The producer thread grabs units and publishes them to the MMA / epilogue warps through a small
+  // shared-memory queue: entry = {first tile, #tiles (0 = end of this CTA's share of batch b, -1 = done), c, b}.
   if (warp == 0) {
     if (lane == 0) {
-      // ============================================================ contraction: TMA producer
+      // ============================================================ contraction: TMA producer + scheduler
       int stage = 0;
       uint32_t phase = 0;
-      int prev_c = -1;
       uint32_t ld = 0;
-      int nc0 = 0, nt0 = 0, nt1 = 0;
-      batch_range(a, 0, nc0, nt0, nt1);
-      for (int b = 0; b < a.n_batches; ++b) {
-        const int c0 = nc0, t0 = nt0, t1 = nt1;
-        if (b + 1 < a.n_batches) batch_range(a, b + 1, nc0, nt0, nt1);   // loads overlap this batch's stream
-        const unsigned long long tw0 = a.trace.rec ? gtime() : 0ull;
-        if (t0 < t1) flag_wait(a.okY + b);               // Y of this batch is complete (and visible to TMA)
-        if (a.trace.rec && (blockIdx.x % 37) == 0) trace_write(a.trace, 301u | (static_cast<unsigned>(b) << 12), tw0, gtime(), 0ull);
-        const int ring_row0 = (b % a.ring) * a.nb - c0;   // ring row of source c = ring_row0 + c
-        int t = t0;
-        Unit un;
-        while (next_unit(a, t1, t, un)) {
-          for (int p = 0; p < a.passes; ++p) {
-            const bool need = a.passes > 1 || un.c != prev_c;
-            for (int ti = 0; ti < un.u; ++ti) {
-              const int e0 = a.tile_e0[un.t + ti];
-              const int box = (a.tile_cnt[un.t + ti] + 15) >> 4;
-              const CUtensorMap* mh = &tmH.m[box - 1];
-              const uint32_t a_bytes = static_cast<uint32_t>(box) * 16u * 128u;
-              for (int s = 0; s < a.nb_slots; ++s) {
-                const int j = p * a.nb_slots + s;
-                if (need && ti == 0) {
-                  mbar_wait(&b_empty[s], (ld & 1u) ^ 1u);
-                  mbar_arrive_expect_tx(&b_full[s], b_chunk_bytes);
-                  tma_load_2d(smem_b + s * b_stride, &tmY, &b_full[s], j * 64, (ring_row0 + un.c) * a.cout, kEvictLast);
-                }
-                mbar_wait(&a_empty[stage], phase ^ 1u);
-                mbar_arrive_expect_tx(&a_full[stage], a_bytes);
-                tma_load_2d(smem_a + stage * kATileBytes, mh, &a_full[stage], 0, j * a.e_pad + e0, kEvictFirst);
-                if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
+      int qi = 0;
+      uint32_t qph = 0;
+      auto publish = [&](int t, int u, int c, int b) {
+        mbar_wait(&q_empty[qi], qph ^ 1u);
+        q_ent[qi] = make_int4(t, u, c, b);
+        mbar_arrive(&q_full[qi]);                         // release: entry visible to the waiters
+        if (++qi == kQueue) { qi = 0; qph ^= 1u; }
+      };
+      // ONE unit counter for the whole application: units are globally ordered by source, so the batch of
+      // a unit follows from its source (b = c / nb); the grab of the next unit is always in flight while the
+      // current one streams (no exposed atomic round trip at batch boundaries).
+      const int n_units = __ldg(a.unit_ptr + a.n_src);
+      int nxt = atomicAdd(a.cntU, 1);
+      int cur_b = -1;
+      while (nxt < n_units) {
+        const int ui = nxt;
+        nxt = atomicAdd(a.cntU, 1);                       // grab the NEXT unit now
+        const int ut = __ldg(a.unit_t + ui), uu = __ldg(a.unit_u + ui);
+        const int uc = a.tile_c[ut];
+        const int b = uc / a.nb;
+        if (b != cur_b) {
+          const unsigned long long tw0 = a.trace.rec ? gtime() : 0ull;
+          flag_wait(a.okY + b);                           // Y of this batch is complete (and visible to TMA)
+          if (a.trace.rec && (blockIdx.x % 37) == 0)
+            trace_write(a.trace, 301u | (static_cast<unsigned>(b) << 12), tw0, gtime(), 0ull);
+          cur_b = b;
+        }
+        const int ring_row0 = (b % a.ring) * a.nb - b * a.nb;
+        publish(ut, uu, uc, b);
+        for (int p = 0; p < a.passes; ++p) {
+          for (int ti = 0; ti < uu; ++ti) {
+            const int e0 = a.tile_e0[ut + ti];
+            const int box = (a.tile_cnt[ut + ti] + 15) >> 4;
+            const CUtensorMap* mh = &tmH.m[box - 1];
+            const uint32_t a_bytes = static_cast<uint32_t>(box) * 16u * 128u;
+            for (int s = 0; s < a.nb_slots; ++s) {
+              const int j = p * a.nb_slots + s;
+              if (ti == 0) {
+                mbar_wait(&b_empty[s], (ld & 1u) ^ 1u);
+                mbar_arrive_expect_tx(&b_full[s], b_chunk_bytes);
+                tma_load_2d(smem_b + s * b_stride, &tmY, &b_full[s], j * 64, (ring_row0 + uc) * a.cout, kEvictLast);
               }
+              mbar_wait(&a_empty[stage], phase ^ 1u);
+              mbar_arrive_expect_tx(&a_full[stage], a_bytes);
+              tma_load_2d(smem_a + stage * kATileBytes, mh, &a_full[stage], 0, j * a.e_pad + e0, kEvictFirst);
+              if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
             }
-            if (need) ++ld;
           }
-          prev_c = un.c;
+          ++ld;
         }
       }
+      publish(0, -1, 0, 0);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -208,111 +218,107 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
       const uint32_t idesc = idesc_f16(FMT, 128, static_cast<uint32_t>(a.cout));
       int stage = 0;
       uint32_t phase = 0;
-      int prev_c = -1;
       uint32_t ld = 0;
       int it = 0;
-      int nc0 = 0, nt0 = 0, nt1 = 0;
-      batch_range(a, 0, nc0, nt0, nt1);
-      for (int b = 0; b < a.n_batches; ++b) {
-        const int t0 = nt0, t1 = nt1;
-        if (b + 1 < a.n_batches) batch_range(a, b + 1, nc0, nt0, nt1);   // prefetch: off the critical path
-        int t = t0;
-        Unit un;
-        while (next_unit(a, t1, t, un)) {
-          const int as = it & 1;
-          mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1u);
-          fence_after_sync();
-          // B is re-loaded for every (unit, pass) when passes > 1, and across batches always (ring slot
-          // changes); within a batch with passes == 1 it stays while the source stays
-          const bool has_next = t < t1;
-          const bool next_same = has_next && a.tile_c[t] == un.c;
-          for (int p = 0; p < a.passes; ++p) {
-            const bool need = a.passes > 1 || un.c != prev_c;
-            const bool release = (p + 1 < a.passes) || a.passes > 1 || !next_same;
-            for (int ti = 0; ti < un.u; ++ti) {
-              const uint32_t d_tmem = tmem_base + (as * kTU + ti) * a.cout;
-              for (int s = 0; s < a.nb_slots; ++s) {
-                if (need && ti == 0) mbar_wait(&b_full[s], ld & 1u);
-                mbar_wait(&a_full[stage], phase);
-                fence_after_sync();
-                const uint64_t adesc = smem_desc_sw128(smem_u32(smem_a + stage * kATileBytes));
-                const uint64_t bdesc = smem_desc_sw128(smem_u32(smem_b + s * b_stride));
+      int qi = 0;
+      uint32_t qph = 0;
+      for (;;) {
+        mbar_wait(&q_full[qi], qph);
+        const int4 en = q_ent[qi];
+        mbar_arrive(&q_empty[qi]);
+        if (++qi == kQueue) { qi = 0; qph ^= 1u; }
+        if (en.y < 0) break;
+        if (en.y == 0) continue;
+        const int as = it & 1;
+        mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1u);
+        fence_after_sync();
+        for (int p = 0; p < a.passes; ++p) {
+          for (int ti = 0; ti < en.y; ++ti) {
+            const uint32_t d_tmem = tmem_base + (as * kTU + ti) * a.cout;
+            for (int s = 0; s < a.nb_slots; ++s) {
+              if (ti == 0) mbar_wait(&b_full[s], ld & 1u);
+              mbar_wait(&a_full[stage], phase);
+              fence_after_sync();
+              const uint64_t adesc = smem_desc_sw128(smem_u32(smem_a + stage * kATileBytes));
+              const uint64_t bdesc = smem_desc_sw128(smem_u32(smem_b + s * b_stride));
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (p | s | k) != 0);
-                umma_commit(&a_empty[stage]);
-                if (release && ti == un.u - 1) umma_commit(&b_empty[s]);
-                if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
-              }
+              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (p | s | k) != 0);
+              umma_commit(&a_empty[stage]);
+              if (ti == en.y - 1) umma_commit(&b_empty[s]);    // B is re-loaded for every (unit, pass)
+              if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
             }
-            if (need) ++ld;
           }
-          umma_commit(&tfull[as]);
-          prev_c = un.c;
-          ++it;
+          ++ld;
         }
-        prev_c = -1;   // a new batch reads a different ring slot: never keep B across batches
+        umma_commit(&tfull[as]);
+        ++it;
       }
     }
   } else if (warp < 6) {
     // ================================================================ contraction: epilogue warps 2..5
     const int quarter = warp % 4;
     int it = 0;
-    int nc0 = 0, nt0 = 0, nt1 = 0;
-    batch_range(a, 0, nc0, nt0, nt1);
-    for (int b = 0; b < a.n_batches; ++b) {
-      const int t0 = nt0, t1 = nt1;
-      if (b + 1 < a.n_batches) batch_range(a, b + 1, nc0, nt0, nt1);
-      int t = t0;
-      Unit un;
-      while (next_unit(a, t1, t, un)) {
-        const int as = it & 1;
-        const int r = quarter * 32 + lane;
-        int d[kTU];
-        float sc[kTU];
-        bool ok[kTU];
+    int qi = 0;
+    uint32_t qph = 0;
+    for (;;) {
+      mbar_wait(&q_full[qi], qph);
+      const int4 en = q_ent[qi];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_empty[qi]);
+      if (++qi == kQueue) { qi = 0; qph ^= 1u; }
+      if (en.y < 0) break;
+      if (en.y == 0) continue;
+      const int as = it & 1;
+      const int r = quarter * 32 + lane;
+      int d[kTU];
+      float sc[kTU];
+      bool ok[kTU];
 #pragma unroll
-        for (int ti = 0; ti < kTU; ++ti) {
-          ok[ti] = ti < un.u && r < a.tile_cnt[un.t + ti];
-          d[ti] = 0;
-          sc[ti] = 1.f;
-          if (ok[ti]) {
-            d[ti] = __ldg(a.dst_sorted + a.tile_e0[un.t + ti] + r);
-            if (a.inv_deg) sc[ti] = __ldg(a.inv_deg + d[ti]);
-          }
+      for (int ti = 0; ti < kTU; ++ti) {
+        ok[ti] = ti < en.y && r < a.tile_cnt[en.x + ti];
+        d[ti] = 0;
+        sc[ti] = 1.f;
+        if (ok[ti]) {
+          d[ti] = __ldg(a.dst_sorted + a.tile_e0[en.x + ti] + r);
+          if (a.inv_deg) sc[ti] = __ldg(a.inv_deg + d[ti]);
         }
-        const float* cv = a.cvec + static_cast<int64_t>(un.c) * a.cout;
-        mbar_wait(&tfull[as], (it >> 1) & 1);
-        fence_after_sync();
+      }
+      const float* cv = a.cvec + static_cast<int64_t>(en.z) * a.cout;
+      mbar_wait(&tfull[as], (it >> 1) & 1);
+      fence_after_sync();
+      if (warp == 2 && lane == 0) {
+        // every MMA that read this unit's Y slice has completed: count the unit; the last unit of batch b
+        // frees the ring slot for the Y pipeline
+        const int c0 = en.w * a.nb;
+        const int target = __ldg(a.unit_ptr + min(c0 + a.nb, a.n_src)) - __ldg(a.unit_ptr + c0);
+        raise_when_all(a.cntC + en.w, a.okC + en.w, target);
+      }
 #pragma unroll
-        for (int ti = 0; ti < kTU; ++ti) {
-          if (ti < un.u) {
-            float* orow = a.out + static_cast<int64_t>(d[ti]) * a.cout;
+      for (int ti = 0; ti < kTU; ++ti) {
+        if (ti < en.y) {
+          float* orow = a.out + static_cast<int64_t>(d[ti]) * a.cout;
 #pragma unroll 1
-            for (int cc = 0; cc < a.cout; cc += 16) {
-              uint32_t v[16];
-              tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * kTU + ti) * a.cout + cc, v);
-              tmem_ld_wait();
-              if (ok[ti]) {
+          for (int cc = 0; cc < a.cout; cc += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * kTU + ti) * a.cout + cc, v);
+            tmem_ld_wait();
+            if (ok[ti]) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float4 cq = __ldg(reinterpret_cast<const float4*>(cv + cc) + q);
-                  red_add_v4(orow + cc + 4 * q, (__uint_as_float(v[4 * q + 0]) + cq.x) * sc[ti],
-                             (__uint_as_float(v[4 * q + 1]) + cq.y) * sc[ti],
-                             (__uint_as_float(v[4 * q + 2]) + cq.z) * sc[ti],
-                             (__uint_as_float(v[4 * q + 3]) + cq.w) * sc[ti]);
-                }
+              for (int q = 0; q < 4; ++q) {
+                const float4 cq = __ldg(reinterpret_cast<const float4*>(cv + cc) + q);
+                red_add_v4(orow + cc + 4 * q, (__uint_as_float(v[4 * q + 0]) + cq.x) * sc[ti],
+                           (__uint_as_float(v[4 * q + 1]) + cq.y) * sc[ti],
+                           (__uint_as_float(v[4 * q + 2]) + cq.z) * sc[ti],
+                           (__uint_as_float(v[4 * q + 3]) + cq.w) * sc[ti]);
               }
             }
           }
         }
-        fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[as]);
-        ++it;
       }
-      // all MMAs of this CTA that read batch b's ring slot have completed (tfull of its last unit observed):
-      // one arrival per CTA; the last CTA frees the ring slot for the Y pipeline
-      if (warp == 2 && lane == 0) raise_when_all(a.cntC + b, a.okC + b, static_cast<int>(gridDim.x));
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      ++it;
     }
   } else if (warp == 6) {
     if (lane == 0) {
@@ -505,6 +511,7 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
   if (s != NNCONV_OK) return s;
   ApplyArgs a;
   a.tile_c = P->tile_c; a.tile_e0 = P->tile_e0; a.tile_cnt = P->tile_cnt; a.tile_ptr = P->tile_ptr;
+  a.unit_ptr = P->unit_ptr; a.unit_t = P->unit_t; a.unit_u = P->unit_u;
   a.dst_sorted = P->dst_sorted; a.inv_deg = aggr_mean ? P->inv_deg : nullptr; a.cvec = cvec; a.out = out;
   a.n_src = P->n_src; a.nb = nb; a.n_batches = n_batches; a.ring = ring;
   a.cout = W->cout; a.nb_slots = as.nb_slots; a.passes = as.passes; a.a_stages = as.a_stages;
@@ -513,6 +520,7 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
   a.y_store_policy = kEvictNormal;
   if (const char* e = getenv("NNCONV_Y_STORE_POLICY")) a.y_store_policy = atoi(e) == 1 ? kEvictLast : atoi(e) == 2 ? kEvictFirst : kEvictNormal;
   a.cntY = flags; a.cntC = flags + flags_stride; a.okY = flags + 2 * flags_stride; a.okC = flags + 3 * flags_stride;
+  a.cntU = flags + 4 * flags_stride;
   {
     TraceHandle th = trace_get();
     a.trace = TraceBuf{th.rec, th.count, th.cap};
@@ -523,10 +531,41 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
     else NNC_CHECK_CUDA(cudaFuncSetAttribute(k_apply_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set[bf] = 1;
   }
+  // Optional (NNCONV_L2_PERSIST=1): pin the Y ring in L2 with an access-policy window on the caller's stream
+  // for the duration of this launch (persisting hits for the ring, everything else streaming).
+  bool window_set = false;
+  if (const char* e = getenv("NNCONV_L2_PERSIST")) {
+    if (atoi(e) > 0) {
+      static int max_persist = -1;
+      if (max_persist < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        if (max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(max_persist));
+      }
+      const size_t ring_bytes = static_cast<size_t>(ring) * nb * NY * 2;
+      if (max_persist > 0) {
+        cudaStreamAttrValue v{};
+        v.accessPolicyWindow.base_ptr = Yring;
+        v.accessPolicyWindow.num_bytes = ring_bytes;
+        v.accessPolicyWindow.hitRatio = ring_bytes <= static_cast<size_t>(max_persist)
+                                            ? 1.0f
+                                            : static_cast<float>(max_persist) / static_cast<float>(ring_bytes);
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        window_set = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess;
+      }
+    }
+  }
   // every CTA must be resident (the flags couple all CTAs): exactly one CTA per SM, never more than #SMs
   const int grid = tc_num_sms();
   if (bf) k_apply_tc<1><<<grid, kThreads, as.smem_bytes, st>>>(tmH, tmY, tmX, tmW, a);
   else k_apply_tc<0><<<grid, kThreads, as.smem_bytes, st>>>(tmH, tmY, tmX, tmW, a);
+  if (window_set) {
+    cudaStreamAttrValue v{};
+    v.accessPolicyWindow.num_bytes = 0;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
+  }
   NNC_CHECK_LAUNCH();
   return NNCONV_OK;
 }

@@ -9,10 +9,14 @@
 // Measured motivation (profiles/r1d): the unfused first layer cost 19.5 ms / step at 241^2 for writing and
 // re-reading 2 x 50 GB of h1, next to 38 ms of tensor-bound hidden GEMM.
 //
-//   warps: 0 TMA producer (A1, W2) | 1 main MMA issuer (TMEM owner) | 2-5 convert (D1 -> A ring) |
-//          6-13 epilogue (D2 -> global) | 14 TMA producer (W1aug chunks) | 15 first-layer MMA issuer
-//   TMEM : D2 [0,256) single buffer (BLOCK_N = 256) | D1 [256,384) two buffers of 64 columns
-//   smem : A1 tile 2 x 16 KB | W1aug chunk ring 2 x 8 KB | (A 16 KB + W2 32 KB) ring x 3
+//   warps: 0 TMA producer (A1, W2) | 1 main MMA issuer (TMEM owner) | 2-9 convert (D1 -> A ring; two warps per
+//          TMEM lane quarter, 32 columns each: one warp set per chunk was a ~650-cycle serial stage) |
+//          10-17 epilogue (D2 -> global) | 18 TMA producer (W1aug chunks) | 19 first-layer MMA issuer
+//   TMEM : D2 [0,384) two buffers (BLOCK_N = 192; the last N tile of a row of tiles may be narrower) |
+//          D1 [384,512) two buffers of 64 columns
+//   smem : A1 tile 2 x 16 KB | W1aug chunk ring 2 x 8 KB | (A 16 KB + W2 24 KB) ring x 4
+// (first version: BLOCK_N = 256 with ONE accumulator and a 3-deep ring ran at 43 % tensor utilisation: the
+//  accumulator drain and the 2-block W2 prefetch distance were exposed; r1e run23)
 // Every synchronisation op of an issuing thread costs ~130 cycles (ncu r1e: the first version, with one
 // thread doing 4 waits + 6 MMAs + 5 commits per 64-column block, ran at 27 % tensor-pipe utilisation), so
 // the barriers are merged: ONE wait + ONE commit per block for each of the two MMA-issuing threads:
@@ -20,8 +24,6 @@
 //   l1_done[b]  <- commit of the first-layer MMAs: D1 buffer b full AND W1 slot b reusable
 //   ab_full[s]  <- W2 tile landed (TMA tx) + 128 convert threads wrote the A tile
 //   ab_empty[s] <- commit of the main MMAs of that stage
-// The epilogue of tile i overlaps the L1 MMAs / conversion of tile i+1; only the first main MMA of tile i+1
-// waits for the accumulator to be drained.
 #include "kernels.h"
 #include "tc05.cuh"
 #include "tmap.h"
@@ -34,13 +36,13 @@ namespace {
 
 using namespace tc05;
 
-constexpr int kBlockN = 256;
+constexpr int kBlockN = 192;                 // 2 x 192 accumulator columns + 2 x 64 D1 columns = 512 TMEM columns
 constexpr int kA1Bytes = 128 * 64 * 2;
 constexpr int kW1Bytes = 64 * 64 * 2;
 constexpr int kABytes = 128 * 64 * 2;
 constexpr int kBBytes = kBlockN * 64 * 2;
-constexpr int kSAB = 3, kSW = 2;       // (A,W2) stage ring; W1aug chunk ring == D1 buffers
-constexpr int kFusedThreads = 16 * 32;
+constexpr int kSAB = 4, kSW = 2;       // (A,W2) stage ring; W1aug chunk ring == D1 buffers
+constexpr int kFusedThreads = 20 * 32;
 constexpr int kFusedSmem = 2 * kA1Bytes + kSW * kW1Bytes + kSAB * (kABytes + kBBytes) + 512;
 
 struct FusedArgs {
@@ -66,13 +68,13 @@ k_mlp12_tc(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUt
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_b + kSAB * kBBytes);
   uint64_t* a1_full = bars;             // [2]
   uint64_t* a1_empty = a1_full + 2;     // [2]
-  uint64_t* l1_ready = a1_empty + 2;    // [2]   1 (TMA arrive.expect_tx) + 4 (convert warps)
+  uint64_t* l1_ready = a1_empty + 2;    // [2]   1 (TMA arrive.expect_tx) + 8 (convert warps)
   uint64_t* l1_done = l1_ready + 2;     // [2]   1 (commit)
-  uint64_t* ab_full = l1_done + 2;      // [kSAB] 1 (TMA) + 128 (convert threads)
+  uint64_t* ab_full = l1_done + 2;      // [kSAB] 1 (TMA) + 256 (convert threads)
   uint64_t* ab_empty = ab_full + kSAB;  // [kSAB] 1 (commit)
-  uint64_t* t_full = ab_empty + kSAB;   // [1]
-  uint64_t* t_empty = t_full + 1;       // [1]   8 (epilogue warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 1);
+  uint64_t* t_full = ab_empty + kSAB;   // [2]
+  uint64_t* t_empty = t_full + 2;       // [2]   8 (epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
 
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int m_blocks = ceil_div(a.M, 128);
@@ -87,12 +89,11 @@ k_mlp12_tc(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUt
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a1_full[i], 1);
       mbar_init(&a1_empty[i], 1);
-      mbar_init(&l1_ready[i], 5);
+      mbar_init(&l1_ready[i], 9);
       mbar_init(&l1_done[i], 1);
     }
-    for (int i = 0; i < kSAB; ++i) { mbar_init(&ab_full[i], 129); mbar_init(&ab_empty[i], 1); }
-    mbar_init(t_full, 1);
-    mbar_init(t_empty, 8);
+    for (int i = 0; i < kSAB; ++i) { mbar_init(&ab_full[i], 257); mbar_init(&ab_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 8); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -103,7 +104,7 @@ k_mlp12_tc(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUt
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d1 = tmem_base + 256;
+  const uint32_t tmem_d1 = tmem_base + 2 * kBlockN;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -111,12 +112,18 @@ k_mlp12_tc(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUt
       int sb = 0;
       uint32_t pb = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int mb = t / n_blocks, nb = t % n_blocks;
-        const int ab = it & 1;
-        mbar_wait(&a1_empty[ab], ((it >> 1) & 1) ^ 1u);
+      auto load_a1 = [&](int tt, int ii) {       // A1 tile of tile tt (the ii-th tile of this CTA)
+        const int ab = ii & 1;
+        mbar_wait(&a1_empty[ab], ((ii >> 1) & 1) ^ 1u);
         mbar_arrive_expect_tx(&a1_full[ab], kA1Bytes);
-        tma_load_2d(s_a1 + ab * kA1Bytes, &tmA1, &a1_full[ab], 0, mb * 128, kEvictNormal);
+        tma_load_2d(s_a1 + ab * kA1Bytes, &tmA1, &a1_full[ab], 0, (tt / n_blocks) * 128, kEvictNormal);
+      };
+      if (static_cast<int>(blockIdx.x) < num_tiles) load_a1(blockIdx.x, 0);
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int nb = t % n_blocks;
+        // the NEXT tile's A1 is requested now (it comes from HBM for every new row of tiles), not after
+        // this tile's W2 stream
+        if (t + static_cast<int>(gridDim.x) < num_tiles) load_a1(t + gridDim.x, it + 1);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&ab_empty[sb], pb ^ 1u);
           mbar_arrive_expect_tx(&ab_full[sb], kBBytes);
@@ -128,26 +135,31 @@ k_mlp12_tc(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUt
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------------------------------------ main MMA issuer: 1 wait + 4 MMA + 1 commit
-      constexpr uint32_t idesc2 = idesc_f16(FMT, 128, kBlockN);
       int sb = 0;
       uint32_t pb = 0;
       int it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        mbar_wait(t_empty, (it & 1) ^ 1u);          // accumulator drained by the epilogue of the previous tile
+        const int nb = t % n_blocks;
+        const int width = min(kBlockN, a.N - nb * kBlockN);      // last N tile of a row may be narrower
+        const uint32_t idesc2 = idesc_f16(FMT, 128, static_cast<uint32_t>(width));
+        const int as = it & 1;
+        mbar_wait(&t_empty[as], ((it >> 1) & 1) ^ 1u);  // this accumulator was drained by the epilogue of tile it-2
+        fence_after_sync();
+        const uint32_t d_tmem = tmem_base + as * kBlockN;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&ab_full[sb], pb);
           fence_after_sync();
           const uint64_t adesc = smem_desc_sw128(smem_u32(s_a + sb * kABytes));
           const uint64_t bdesc = smem_desc_sw128(smem_u32(s_b + sb * kBBytes));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc2, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc2, (kb | k) != 0);
           umma_commit(&ab_empty[sb]);
           if (++sb == kSAB) { sb = 0; pb ^= 1u; }
         }
-        umma_commit(t_full);
+        umma_commit(&t_full[as]);
       }
     }
-  } else if (warp == 14) {
+  } else if (warp == 18) {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer: W1aug chunks, slot = g & 1
       uint32_t g = 0;
@@ -160,7 +172,7 @@ k_mlp12_tc(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 15) {
+  } else if (warp == 19) {
     if (lane == 0) {
       // ------------------------------------------------------------ first-layer MMA issuer (runs ahead of the
       // main GEMM by the two D1 buffers; throttled only by l1_ready): 1 wait + l1_ksteps MMA + 1 commit
@@ -184,9 +196,10 @@ k_mlp12_tc(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUt
         umma_commit(&a1_empty[ab]);                 // all first-layer MMAs of this tile have been issued
       }
     }
-  } else if (warp < 6) {
-    // ---------------------------------------------------------------- convert warps 2..5: D1 -> relu -> A ring
+  } else if (warp < 10) {
+    // ---------------------------------------------------------------- convert warps 2..9: D1 -> relu -> A ring
     const int quarter = warp % 4;
+    const int chalf = (warp - 2) / 4;             // which 32 of the chunk's 64 columns
     const int r = quarter * 32 + lane;            // tile row owned by this thread
     int sa = 0;
     uint32_t pa = 0;
@@ -200,23 +213,22 @@ k_mlp12_tc(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUt
         const uint32_t b = g & 1u;
         mbar_wait(&l1_done[b], (g >> 1) & 1u);
         fence_after_sync();
-        uint32_t v[64];
-        const uint32_t ta = tmem_d1 + (static_cast<uint32_t>(quarter * 32) << 16) + b * 64;
-        tmem_ld32(ta, v);
-        tmem_ld32(ta + 32, v + 32);
+        uint32_t v[32];
+        tmem_ld32(tmem_d1 + (static_cast<uint32_t>(quarter * 32) << 16) + b * 64 + chalf * 32, v);
+        mbar_wait(&ab_empty[sa], pa ^ 1u);         // (overlaps the TMEM load) main MMAs that last read this A stage are done
         tmem_ld_wait();
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&l1_ready[b]);  // D1 buffer b may be overwritten (chunk g+2)
-        mbar_wait(&ab_empty[sa], pa ^ 1u);         // the main MMAs that last read this A stage have completed
         uint8_t* row = s_a + sa * kABytes + r * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {              // 8 chunks of 8 elements (16 B); physical chunk = j ^ (r & 7)
+        for (int jj = 0; jj < 4; ++jj) {           // 4 chunks of 8 elements (16 B); physical chunk = j ^ (r & 7)
+          const int j = chalf * 4 + jj;
           uint32_t pk[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float f0 = fmaxf(__uint_as_float(v[j * 8 + 2 * q]), 0.f);
-            const float f1 = fmaxf(__uint_as_float(v[j * 8 + 2 * q + 1]), 0.f);
+            const float f0 = fmaxf(__uint_as_float(v[jj * 8 + 2 * q]), 0.f);
+            const float f1 = fmaxf(__uint_as_float(v[jj * 8 + 2 * q + 1]), 0.f);
             if (FMT == 0) {
               __half2 hh = __floats2half2_rn(f0, f1);
               pk[q] = *reinterpret_cast<uint32_t*>(&hh);
@@ -233,30 +245,34 @@ k_mlp12_tc(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUt
       }
     }
   } else {
-    // ---------------------------------------------------------------- epilogue warps 6..13
+    // ---------------------------------------------------------------- epilogue warps 10..17
     const int quarter = warp % 4;
-    const int half = (warp - 6) / 4;
-    constexpr int kChunks = kBlockN / 64;
+    const int half = (warp - 10) / 4;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int mb = t / n_blocks, nb = t % n_blocks;
-      mbar_wait(t_full, it & 1);
+      const int width = min(kBlockN, a.N - nb * kBlockN);
+      const int hw = width / 2;                      // columns of this warp (multiple of 32)
+      const int chunks = hw / 32;
+      const int as = it & 1;
+      mbar_wait(&t_full[as], (it >> 1) & 1);
       fence_after_sync();
       const int row = mb * 128 + quarter * 32 + lane;
       const bool row_ok = row < a.M;
       uint16_t* crow = reinterpret_cast<uint16_t*>(a.C) + static_cast<int64_t>(row) * a.ldc;
       const int64_t grow = a.c_row0 + row;
-      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + half * (kBlockN / 2);
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kBlockN + half * hw;
       uint32_t v[2][32];
       tmem_ld32(tbase, v[0]);
       tmem_ld_wait();
 #pragma unroll
-      for (int cc = 0; cc < kChunks; ++cc) {
-        if (cc + 1 < kChunks) tmem_ld32(tbase + (cc + 1) * 32, v[(cc + 1) & 1]);
-        const int col0 = nb * kBlockN + half * (kBlockN / 2) + cc * 32;
-        uint32_t packed[16];
-        if (col0 < a.N && row_ok) {
+      for (int cc = 0; cc < kBlockN / 64; ++cc) {        // static bound keeps v[] in registers
+        if (cc >= chunks) break;
+        if (cc + 1 < chunks) tmem_ld32(tbase + (cc + 1) * 32, v[(cc + 1) & 1]);
+        const int col0 = nb * kBlockN + half * hw + cc * 32;
+        if (row_ok) {
           const uint32_t* vv = v[cc & 1];
+          uint32_t packed[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float f0 = __uint_as_float(vv[2 * j]) + __ldg(a.bias + col0 + 2 * j);
@@ -271,14 +287,6 @@ k_mlp12_tc(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUt
               packed[j] = *reinterpret_cast<uint32_t*>(&hh);
             }
           }
-        }
-        if (cc + 1 < kChunks) tmem_ld_wait();
-        if (cc + 1 == kChunks) {                   // every TMEM read of this warp is done: free the accumulator
-          fence_before_sync();                     // BEFORE the global stores, so the next tile's MMAs start early
-          __syncwarp();
-          if (lane == 0) mbar_arrive(t_empty);
-        }
-        if (col0 < a.N && row_ok) {
           uint16_t* dst = a.chunk_rows_pad > 0
                               ? reinterpret_cast<uint16_t*>(a.C) +
                                     (static_cast<int64_t>(col0 >> 6) * a.chunk_rows_pad + grow) * 64 + (col0 & 63)
@@ -286,7 +294,11 @@ k_mlp12_tc(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUt
           st_global_v8(dst, packed);
           st_global_v8(dst + 16, packed + 8);
         }
+        if (cc + 1 < chunks) tmem_ld_wait();
       }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[as]);
     }
   }
   fence_before_sync();

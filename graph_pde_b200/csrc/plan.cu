@@ -38,19 +38,21 @@ __global__ void k_keys(const int64_t* __restrict__ src, int64_t E, int* __restri
 }
 
 __global__ void k_node_flags(const int* __restrict__ outdeg, int64_t N, int* __restrict__ nz, int* __restrict__ nt,
-                             int* __restrict__ maxdeg) {
+                             int* __restrict__ nu, int* __restrict__ maxdeg) {
   int64_t n = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (n >= N) return;
   int d = outdeg[n];
   nz[n] = d > 0 ? 1 : 0;
   nt[n] = (d + kTileEdges - 1) / kTileEdges;
+  nu[n] = (nt[n] + 1) / 2;
   if (d > 0) atomicMax(maxdeg, d);
 }
 
 __global__ void k_compact(const int* __restrict__ outdeg, const int* __restrict__ rowptr, const int* __restrict__ cpos,
-                          const int* __restrict__ tpos, int64_t N, int* __restrict__ src_nodes,
-                          int* __restrict__ group_ptr, int* __restrict__ tile_ptr, int* __restrict__ tile_c,
-                          int* __restrict__ tile_e0, int* __restrict__ tile_cnt) {
+                          const int* __restrict__ tpos, const int* __restrict__ upos, int64_t N,
+                          int* __restrict__ src_nodes, int* __restrict__ group_ptr, int* __restrict__ tile_ptr,
+                          int* __restrict__ tile_c, int* __restrict__ tile_e0, int* __restrict__ tile_cnt,
+                          int* __restrict__ unit_ptr, int* __restrict__ unit_t, int* __restrict__ unit_u) {
   int64_t n = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (n >= N) return;
   int d = outdeg[n];
@@ -65,17 +67,27 @@ __global__ void k_compact(const int* __restrict__ outdeg, const int* __restrict_
     tile_e0[t0 + i] = e0 + i * kTileEdges;
     tile_cnt[t0 + i] = min(kTileEdges, d - i * kTileEdges);
   }
+  const int u0 = upos[n];
+  unit_ptr[c] = u0;
+  for (int i = 0; i < (nt + 1) / 2; ++i) {
+    unit_t[u0 + i] = t0 + 2 * i;
+    unit_u[u0 + i] = min(2, nt - 2 * i);
+  }
 }
 
-__global__ void k_tail(int* group_ptr, int* tile_ptr, const int* cpos, const int* tpos, const int* outdeg,
-                       int64_t N, int64_t E, int* counts) {
+__global__ void k_tail(int* group_ptr, int* tile_ptr, int* unit_ptr, const int* cpos, const int* tpos,
+                       const int* upos, const int* outdeg, int64_t N, int64_t E, int* counts) {
   // totals = exclusive-scan value at N-1 plus the last element
   int S = cpos[N - 1] + (outdeg[N - 1] > 0 ? 1 : 0);
   int T = tpos[N - 1] + (outdeg[N - 1] + kTileEdges - 1) / kTileEdges;
+  const int ntl = (outdeg[N - 1] + kTileEdges - 1) / kTileEdges;
+  const int U = upos[N - 1] + (ntl + 1) / 2;
   group_ptr[S] = static_cast<int>(E);
   tile_ptr[S] = T;
+  unit_ptr[S] = U;
   counts[0] = S;
   counts[1] = T;
+  counts[3] = U;
 }
 
 __global__ void k_sorted_dst(const int64_t* __restrict__ dst, const int* __restrict__ perm, int64_t E,
@@ -108,7 +120,7 @@ size_t cub_sort_bytes(int64_t n) {
 
 struct PlanLayout {
   // persistent
-  int *perm, *dst_sorted, *src_nodes, *group_ptr, *tile_ptr, *tile_c, *tile_e0, *tile_cnt;
+  int *perm, *dst_sorted, *src_nodes, *group_ptr, *tile_ptr, *tile_c, *tile_e0, *tile_cnt, *unit_ptr, *unit_t, *unit_u;
   float* inv_deg;
   size_t ws_bytes;
 };
@@ -126,13 +138,16 @@ PlanLayout carve_plan(void* ws, int64_t E, int64_t N) {
   L.tile_c = c.take<int>(Tmax);
   L.tile_e0 = c.take<int>(Tmax);
   L.tile_cnt = c.take<int>(Tmax);
+  L.unit_ptr = c.take<int>(Smax + 1);
+  L.unit_t = c.take<int>(Tmax);
+  L.unit_u = c.take<int>(Tmax);
   L.inv_deg = c.take<float>(N + 1);
   L.ws_bytes = c.off;
   return L;
 }
 
 struct TmpLayout {
-  int *outdeg, *indeg, *rowptr, *nz, *nt, *cpos, *tpos, *flags, *counts, *keys_in, *keys_out, *vals_in;
+  int *outdeg, *indeg, *rowptr, *nz, *nt, *nu, *cpos, *tpos, *upos, *flags, *counts, *keys_in, *keys_out, *vals_in;
   void* cub_tmp;
   size_t cub_bytes;
   size_t bytes;
@@ -146,6 +161,8 @@ TmpLayout carve_tmp(void* tmp, int64_t E, int64_t N) {
   L.rowptr = c.take<int>(N + 1);
   L.nz = c.take<int>(N + 1);
   L.nt = c.take<int>(N + 1);
+  L.nu = c.take<int>(N + 1);
+  L.upos = c.take<int>(N + 1);
   L.cpos = c.take<int>(N + 1);
   L.tpos = c.take<int>(N + 1);
   L.flags = c.take<int>(8);
@@ -194,6 +211,10 @@ int plan_build(Plan* P, const int64_t* row0, const int64_t* row1, int64_t E, int
   P->tile_c = L.tile_c;
   P->tile_e0 = L.tile_e0;
   P->tile_cnt = L.tile_cnt;
+  P->unit_ptr = L.unit_ptr;
+  P->unit_t = L.unit_t;
+  P->unit_u = L.unit_u;
+  P->n_units = 0;
   P->inv_deg = L.inv_deg;
   P->n_src = 0;
   P->n_tiles = 0;
@@ -226,16 +247,19 @@ int plan_build(Plan* P, const int64_t* row0, const int64_t* row1, int64_t E, int
   }
   size_t cb = T.cub_bytes;
   NNC_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(T.cub_tmp, cb, T.outdeg, T.rowptr, static_cast<int>(N), st));
-  k_node_flags<<<(unsigned)ceil_div64(N, TB), TB, 0, st>>>(T.outdeg, N, T.nz, T.nt, T.counts + 2);
+  k_node_flags<<<(unsigned)ceil_div64(N, TB), TB, 0, st>>>(T.outdeg, N, T.nz, T.nt, T.nu, T.counts + 2);
   NNC_CHECK_LAUNCH();
   cb = T.cub_bytes;
   NNC_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(T.cub_tmp, cb, T.nz, T.cpos, static_cast<int>(N), st));
   cb = T.cub_bytes;
   NNC_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(T.cub_tmp, cb, T.nt, T.tpos, static_cast<int>(N), st));
-  k_compact<<<(unsigned)ceil_div64(N, TB), TB, 0, st>>>(T.outdeg, T.rowptr, T.cpos, T.tpos, N, L.src_nodes,
-                                                        L.group_ptr, L.tile_ptr, L.tile_c, L.tile_e0, L.tile_cnt);
+  cb = T.cub_bytes;
+  NNC_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(T.cub_tmp, cb, T.nu, T.upos, static_cast<int>(N), st));
+  k_compact<<<(unsigned)ceil_div64(N, TB), TB, 0, st>>>(T.outdeg, T.rowptr, T.cpos, T.tpos, T.upos, N, L.src_nodes,
+                                                        L.group_ptr, L.tile_ptr, L.tile_c, L.tile_e0, L.tile_cnt,
+                                                        L.unit_ptr, L.unit_t, L.unit_u);
   NNC_CHECK_LAUNCH();
-  k_tail<<<1, 1, 0, st>>>(L.group_ptr, L.tile_ptr, T.cpos, T.tpos, T.outdeg, N, E, T.counts);
+  k_tail<<<1, 1, 0, st>>>(L.group_ptr, L.tile_ptr, L.unit_ptr, T.cpos, T.tpos, T.upos, T.outdeg, N, E, T.counts);
   NNC_CHECK_LAUNCH();
   if (E > 0) {
     k_sorted_dst<<<(unsigned)ceil_div64(E, TB), TB, 0, st>>>(dst, P->perm, E, L.dst_sorted);
@@ -243,12 +267,13 @@ int plan_build(Plan* P, const int64_t* row0, const int64_t* row1, int64_t E, int
   }
   k_inv_deg<<<(unsigned)ceil_div64(N, TB), TB, 0, st>>>(T.indeg, N, L.inv_deg);
   NNC_CHECK_LAUNCH();
-  int h_counts[3] = {0, 0, 0};
-  NNC_CHECK_CUDA(cudaMemcpyAsync(h_counts, T.counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  int h_counts[4] = {0, 0, 0, 0};
+  NNC_CHECK_CUDA(cudaMemcpyAsync(h_counts, T.counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
   NNC_CHECK_CUDA(cudaStreamSynchronize(st));
   P->n_src = h_counts[0];
   P->n_tiles = h_counts[1];
   P->max_out_deg = h_counts[2];
+  P->n_units = h_counts[3];
   return NNCONV_OK;
 }
 

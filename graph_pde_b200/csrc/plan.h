@@ -25,6 +25,10 @@ struct Plan {
   const int* tile_c;      // [T]
   const int* tile_e0;     // [T]
   const int* tile_cnt;    // [T]
+  const int* unit_ptr;    // [S+1] first unit of source c (unit = <= 2 consecutive tiles of one source)
+  const int* unit_t;      // [U] first tile of the unit
+  const int* unit_u;      // [U] tiles in the unit (1 or 2)
+  int n_units;
   const float* inv_deg;   // [N] 1/max(in_degree,1)
   const int* h_tile_ptr;  // HOST mirror of tile_ptr ([S+1]) owned by the C handle
 };

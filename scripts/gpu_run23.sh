@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+echo "=== tests" ; timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -6
+run() { timeout 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']/1e6,1), round(d['ms_per_step'],2), round(d['e2e']['value']/1e6,1), {k:round(v['ms'],1) for k,v in d['kernel_ms_per_step'].items() if v['ms']>0}, d['clocks']['sm_mhz'], [(r['kernel'][:10], round(r['frac'],3)) for r in d['roofline_kernels']])"; }
+echo "=== default"; run
+echo "=== unfused12"; NNCONV_NO_FUSE12=1 run
+echo "=== darcy85"; NNCONV_BENCH_WORKLOAD=darcy85 run
