@@ -23,6 +23,7 @@ SYMBOLS = [
     'nnconv_weights_destroy', 'nnconv_weights_tc_supported', 'nnconv_edge_features_sizes',
     'nnconv_edge_features', 'nnconv_apply_sizes', 'nnconv_apply', 'nnconv_gemm_16b',
     'nnconv_profile_begin', 'nnconv_profile_end', 'nnconv_debug_trace_dump',
+    'nnconv_backward_sizes', 'nnconv_backward',
 ]
 
 
@@ -76,6 +77,9 @@ def lib():
     L.nnconv_apply.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_sz, c_vp, P(c_i64)]
     L.nnconv_gemm_16b.argtypes = [c_int, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp]
     L.nnconv_profile_end.argtypes = [P(ctypes.c_double), P(c_i64), c_int]
+    L.nnconv_backward_sizes.argtypes = [c_vp, c_vp, c_sz, P(c_sz)]
+    L.nnconv_backward.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, P(c_vp), P(c_vp), c_vp, c_vp, c_vp,
+                                  c_sz, c_vp]
     L.nnconv_debug_trace_dump.argtypes = [P(ctypes.c_ulonglong), ctypes.c_uint, P(ctypes.c_uint)]
     for name in SYMBOLS:
         getattr(L, name)

@@ -455,7 +455,7 @@ using namespace nnc;
 
 struct nnconv_plan {
   Plan p;
-  int* h_tile_ptr_storage;
+  int* h_tile_ptr_storage;     // [2*(S+1)]: tile_ptr mirror, then group_ptr mirror
 };
 struct nnconv_weights {
   Weights w;
@@ -488,10 +488,13 @@ int nnconv_plan_create(const int64_t* row0, const int64_t* row1, int64_t E, int6
   if (s != NNCONV_OK) { delete h; return s; }
   // host mirror of tile_ptr (S+1 ints) so that batch tile ranges need no device read later
   const int S = h->p.n_src;
-  h->h_tile_ptr_storage = new (std::nothrow) int[static_cast<size_t>(S) + 1];
+  h->h_tile_ptr_storage = new (std::nothrow) int[2 * (static_cast<size_t>(S) + 1)];
   if (!h->h_tile_ptr_storage) { delete h; set_error("out of host memory"); return NNCONV_ERR_ARG; }
   cudaError_t e = cudaMemcpyAsync(h->h_tile_ptr_storage, h->p.tile_ptr, (static_cast<size_t>(S) + 1) * sizeof(int),
                                   cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(h->h_tile_ptr_storage + S + 1, h->p.group_ptr, (static_cast<size_t>(S) + 1) * sizeof(int),
+                        cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) {
     set_error("plan: copying tile_ptr failed: %s", cudaGetErrorString(e));
@@ -500,6 +503,7 @@ int nnconv_plan_create(const int64_t* row0, const int64_t* row1, int64_t E, int6
     return NNCONV_ERR_CUDA;
   }
   h->p.h_tile_ptr = h->h_tile_ptr_storage;
+  h->p.h_group_ptr = h->h_tile_ptr_storage + S + 1;
   *out = h;
   return NNCONV_OK;
 }
@@ -579,6 +583,24 @@ int nnconv_apply(const nnconv_plan_t* plan, const nnconv_weights_t* w, const voi
               "aggr must be add (0) or mean (1); 'max' is used by no call site of the reference and is not built");
   return apply(&plan->p, &w->w, h, x, root, bias, aggr == NNCONV_AGGR_MEAN, out, ws, ws_bytes,
                static_cast<cudaStream_t>(stream), launches);
+}
+
+int nnconv_backward_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t want_bytes, size_t* ws_bytes) {
+  NNC_REQUIRE(plan && w && ws_bytes, NNCONV_ERR_ARG, "null pointer");
+  NNC_REQUIRE(w->w.prec == PREC_FP32, NNCONV_ERR_ARG, "backward needs weights prepared with NNCONV_PREC_FP32");
+  *ws_bytes = backward_ws_bytes(&plan->p, &w->w, want_bytes);
+  return NNCONV_OK;
+}
+
+int nnconv_backward(const nnconv_plan_t* plan, const nnconv_weights_t* w, const float* edge_attr, const float* x,
+                    const float* root, int aggr, const float* grad_out, float* grad_x, float* const* grad_W,
+                    float* const* grad_b, float* grad_root, float* grad_bias, void* ws, size_t ws_bytes,
+                    void* stream) {
+  NNC_REQUIRE(plan && w && x && grad_out && grad_x && grad_W && grad_b, NNCONV_ERR_ARG, "null pointer");
+  NNC_REQUIRE(aggr == NNCONV_AGGR_ADD || aggr == NNCONV_AGGR_MEAN, NNCONV_ERR_UNSUPPORTED, "aggr must be add or mean");
+  NNC_REQUIRE((root == nullptr) == (grad_root == nullptr), NNCONV_ERR_ARG, "root / grad_root must both be given or both be NULL");
+  return backward_fp32(&plan->p, &w->w, edge_attr, x, root, aggr == NNCONV_AGGR_MEAN, grad_out, grad_x, grad_W,
+                       grad_b, grad_root, grad_bias, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int nnconv_profile_begin(void) {

@@ -31,6 +31,7 @@ struct Plan {
   int n_units;
   const float* inv_deg;   // [N] 1/max(in_degree,1)
   const int* h_tile_ptr;  // HOST mirror of tile_ptr ([S+1]) owned by the C handle
+  const int* h_group_ptr; // HOST mirror of group_ptr ([S+1]) owned by the C handle
 };
 
 void plan_sizes(int64_t E, int64_t N, size_t* ws_bytes, size_t* tmp_bytes);
@@ -69,5 +70,11 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
 size_t apply_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes);
 int apply(const Plan* P, const Weights* W, const void* h, const float* x, const float* root, const float* bias,
           int aggr_mean, float* out, void* ws, size_t ws_bytes, cudaStream_t st, int64_t* launches);
+
+// backward of one application (fp32 CUDA-core path), backward.cu
+size_t backward_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes);
+int backward_fp32(const Plan* P, const Weights* W, const float* edge_attr, const float* x, const float* root,
+                  int aggr_mean, const float* gout, float* dx, float* const* dWs, float* const* dbs, float* droot,
+                  float* dbias, void* ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace nnc

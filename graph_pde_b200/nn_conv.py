@@ -39,6 +39,7 @@ _PLAN_CACHE = collections.OrderedDict()
 _PLAN_CACHE_MAX = int(os.environ.get('NNCONV_B200_PLAN_CACHE', '64'))
 _Y_BYTES = int(os.environ.get('NNCONV_B200_Y_BYTES', str(48 << 20)))       # Y ring: 3 x 128 sources at out=64, Kp=1024
 _EF_WS_BYTES = int(os.environ.get('NNCONV_B200_EF_WS_BYTES', str(1 << 30)))  # hidden-layer ping-pong chunk
+_BWD_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_WS_BYTES', str(2 << 30)))  # backward: activations per batch
 
 
 def default_precision():
@@ -171,15 +172,26 @@ class _Prepared(object):
 
 
 class _NNConvFunction(torch.autograd.Function):
+    """Differentiable wrapper: forward = the configured precision path, backward = nnconv_backward (fp32
+    CUDA-core kernels, csrc/backward.cu).  Gradients flow to x, the edge-MLP Linear weights/biases, root and
+    bias; edge_index / edge_attr are leaf inputs in every reference script and get none."""
+
     @staticmethod
     def forward(ctx, module, x, edge_index, edge_attr, *params):
+        ctx.module = module
+        ctx.edge_index = edge_index
+        ctx.save_for_backward(x, edge_attr)
         return module._forward_impl(x, edge_index, edge_attr)
 
     @staticmethod
     def backward(ctx, grad_out):
-        raise NotImplementedError(
-            'graph_pde_b200.NNConv: the backward pass of the B200 kernel path is not built yet '
-            '(SURVEY 8(a) row a11); run the forward under torch.no_grad()')
+        module = ctx.module
+        x, edge_attr = ctx.saved_tensors
+        grads = module._backward_impl(x, ctx.edge_index, edge_attr, grad_out)
+        # order of *params in forward(): list(module.parameters())
+        by_id = {id(p): g for p, g in grads['params']}
+        return (None, grads['x'] if ctx.needs_input_grad[1] else None, None, None) + tuple(
+            by_id.get(id(p)) for p in module.parameters())
 
 
 class NNConv_old(torch.nn.Module):
@@ -242,6 +254,8 @@ class NNConv_old(torch.nn.Module):
         needs_grad = torch.is_grad_enabled() and (
             x.requires_grad or any(p.requires_grad for p in self.parameters()))
         if needs_grad:
+            if self.aggr == 'max':
+                raise NotImplementedError("aggr='max' is used by no call site of the reference and is not built")
             return _NNConvFunction.apply(self, x, edge_index, pseudo, *list(self.parameters()))
         return self._forward_impl(x, edge_index, pseudo)
 
@@ -317,6 +331,47 @@ class NNConv_old(torch.nn.Module):
             stats['launches'] += n_l.value
             stats['applies'] += 1
         return out
+
+
+    def _backward_impl(self, x, edge_index, pseudo, grad_out):
+        if pseudo.requires_grad:
+            raise NotImplementedError('gradients w.r.t. edge_attr are not built (leaf input in the reference)')
+        L = _lib.lib()
+        with torch.cuda.device(x.device):
+            x32 = x.detach().contiguous().float()
+            ea32 = pseudo.detach().contiguous().float()
+            g32 = grad_out.detach().contiguous().float()
+            n = x32.size(0)
+            plan = get_plan(edge_index, n, self.flow)
+            linears = _linear_chain(self.nn)
+            key = ('fp32',) + tuple((l.weight.data_ptr(), l.weight._version, l.bias.data_ptr(), l.bias._version)
+                                    for l in linears)
+            if getattr(self, '_prepared32_key', None) != key:
+                self._prepared32 = _Prepared(linears, self.in_channels, self.out_channels, 'fp32')
+                self._prepared32_key = key
+            prep = self._prepared32
+            ws_b = ctypes.c_size_t()
+            _lib.check(L.nnconv_backward_sizes(plan.handle, prep.handle, _BWD_WS_BYTES, ctypes.byref(ws_b)))
+            ws = torch.empty(ws_b.value, dtype=torch.uint8, device=x.device)
+            dx = torch.empty_like(x32)
+            dws = [torch.empty_like(l.weight, dtype=torch.float32) for l in linears]
+            dbs = [torch.empty_like(l.bias, dtype=torch.float32) for l in linears]
+            droot = torch.empty_like(self.root, dtype=torch.float32) if self.root is not None else None
+            dbias = torch.empty_like(self.bias, dtype=torch.float32) if self.bias is not None else None
+            nl = len(linears)
+            wp = (ctypes.c_void_p * nl)(*[t.data_ptr() for t in dws])
+            bp = (ctypes.c_void_p * nl)(*[t.data_ptr() for t in dbs])
+            root = self.root.detach().contiguous().float() if self.root is not None else None
+            _lib.check(L.nnconv_backward(plan.handle, prep.handle, _ptr(ea32), _ptr(x32), _ptr(root),
+                                         _lib.AGGR[self.aggr], _ptr(g32), _ptr(dx), wp, bp, _ptr(droot), _ptr(dbias),
+                                         _ptr(ws), ws_b.value, _stream_ptr(x.device)))
+            stats['backwards'] = stats.get('backwards', 0) + 1
+        params = [(l.weight, dw) for l, dw in zip(linears, dws)] + [(l.bias, db) for l, db in zip(linears, dbs)]
+        if self.root is not None:
+            params.append((self.root, droot))
+        if self.bias is not None:
+            params.append((self.bias, dbias))
+        return {'x': dx.to(x.dtype), 'params': params}
 
 
 class NNConv(NNConv_old):

@@ -107,6 +107,17 @@ int nnconv_apply(const nnconv_plan_t* plan, const nnconv_weights_t* w, const voi
                  const float* root, const float* bias, int aggr, float* out, void* ws, size_t ws_bytes, void* stream,
                  int64_t* launches /*nullable*/);
 
+/* ---- backward of one application (what autograd generates for nn_conv.py:267-282 + utilities.py:223-227):
+ * grad_x [N,in], grad_W[l] / grad_b[l] in the torch.nn.Linear layouts of the edge MLP, grad_root [in,out],
+ * grad_bias [out] (NULL when the module has no root / bias).  fp32 CUDA-core path for arbitrary shapes: `w`
+ * must have been created with NNCONV_PREC_FP32.  Gradients are WRITTEN (not accumulated). edge_attr and
+ * edge_index receive no gradient (they are leaf inputs in every reference script). ------------------------- */
+int nnconv_backward_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t want_bytes, size_t* ws_bytes);
+int nnconv_backward(const nnconv_plan_t* plan, const nnconv_weights_t* w, const float* edge_attr, const float* x,
+                    const float* root, int aggr, const float* grad_out, float* grad_x, float* const* grad_W,
+                    float* const* grad_b, float* grad_root, float* grad_bias, void* ws, size_t ws_bytes,
+                    void* stream);
+
 /* ---- measurement hook (bench.py): while enabled, every kernel launch is bracketed by CUDA events on its
  * stream; profile_end synchronises the device and returns summed milliseconds / launch counts per kernel
  * class: 0 first MLP layer, 1 hidden-layer GEMM, 2 per-node prologue, 3 per-source Y GEMM (unfused path),
