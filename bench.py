@@ -211,9 +211,14 @@ def main():
         dev_ea.append(ea_i)
         host_x.append(x_i.cpu().pin_memory())
         host_ea.append(ea_i.cpu().pin_memory())
-    stage_x = torch.empty_like(dev_x[0])
-    stage_ea = torch.empty_like(dev_ea[0])
+    # e2e staging: two device buffers, filled from pinned host memory on a copy stream while the previous step
+    # computes (what any input pipeline does); every step's copy is inside the timed region.
+    stage = [(torch.empty_like(dev_x[0]), torch.empty_like(dev_ea[0])) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
     host_out = torch.empty(N, 1).pin_memory()
+    e2e_state = {'prefetched': -1}
 
     class D(object):
         pass
@@ -224,13 +229,25 @@ def main():
             x0 = model.fc1(dev_x[i % n_samples])
             return model.conv_stack(x0, ei, dev_ea[i % n_samples])
 
+    def prefetch(i):
+        sx, sea = stage[i % 2]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])   # the step that last used this buffer has finished with it
+            sx.copy_(host_x[i % n_samples], non_blocking=True)
+            sea.copy_(host_ea[i % n_samples], non_blocking=True)   # bumps _version -> edge features recomputed
+            ready[i % 2].record(copy_stream)
+        e2e_state['prefetched'] = i
+
     def step_e2e(i):
-        stage_x.copy_(host_x[i % n_samples], non_blocking=True)
-        stage_ea.copy_(host_ea[i % n_samples], non_blocking=True)     # bumps _version -> features recomputed
+        if e2e_state['prefetched'] < i:
+            prefetch(i)
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        prefetch(i + 1)                               # next step's inputs travel while this step computes
         d = D()
-        d.x, d.edge_index, d.edge_attr = stage_x, ei, stage_ea
+        d.x, d.edge_index, d.edge_attr = stage[i % 2][0], ei, stage[i % 2][1]
         with torch.no_grad():
             out = model(d)
+        consumed[i % 2].record()
         host_out.copy_(out, non_blocking=False)
         return host_out
 
@@ -239,10 +256,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, pre=None):
         for i in range(warmup):
             fn(i)
         barrier()
+        if pre is not None:
+            pre()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for i in range(steps):
@@ -264,7 +283,11 @@ def main():
     launches_timed = int(round(launches * args.steps / float(args.steps + max(args.warmup, 3))))
     value = world * E * T * args.steps / (ms_total * 1e-3)
 
-    ms_e2e = timed(step_e2e, args.steps, 1)
+    def e2e_reset():          # nothing copied outside the timed region: the first timed step fetches its own inputs
+        copy_stream.synchronize()
+        e2e_state['prefetched'] = -1
+
+    ms_e2e = timed(step_e2e, args.steps, 1, pre=e2e_reset)
     e2e_value = world * E * T * args.steps / (ms_e2e * 1e-3)
     h2d = host_x[0].numel() * 4 + host_ea[0].numel() * 4
     d2h = host_out.numel() * 4
@@ -308,8 +331,9 @@ def main():
                     dtype=args.precision, data='synthetic', config=config, clocks=clocks,
                     e2e=dict(value=e2e_value, unit='edge-apps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=ms_e2e / args.steps,
-                             note='x and edge_attr from pinned host memory every step; edge_index (shared mesh) '
-                                  'resident; output [N,1] read back'),
+                             note='x and edge_attr from pinned host memory every step (double-buffered prefetch on a '
+                                  'copy stream overlaps the next step\'s H2D with this step\'s kernels); edge_index '
+                                  '(shared mesh) resident; output [N,1] read back'),
                     gpu_launches=launches_timed, roofline=dominant,
                     roofline_kernels=[rf_conv, rf_gemm], kernel_ms_per_step=prof,
                     roofline_survey=dict(formA_tensor_frac=value / world * f_alg / (pk['tf_sustained'] * 1e12),
