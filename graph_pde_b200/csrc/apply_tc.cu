@@ -33,8 +33,6 @@ constexpr int kMaxSlots = 16;
 constexpr int kMaxAStages = 8;
 constexpr int kTU = 2;
 constexpr int kATileBytes = 128 * 64 * 2;
-constexpr int kYBlockN = 128;
-constexpr int kYStageBytes = kATileBytes + kYBlockN * 64 * 2;   // Xc tile + W3p tile
 constexpr int kYStages = 2;
 constexpr int kThreads = 384;
 constexpr int kQueue = 8;                  // unit queue between the scheduler and the MMA / epilogue warps
@@ -79,10 +77,11 @@ __device__ __forceinline__ void raise_when_all(int* cnt, int* ok, int target) {
   }
 }
 
-template <int FMT>
+template <int FMT, int kYBlockN>
 __global__ void __launch_bounds__(kThreads, 1)
 k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMap tmY,
            const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, ApplyArgs a) {
+  constexpr int kYStageBytes = kATileBytes + kYBlockN * 64 * 2;   // Xc tile + W3p tile
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int b_chunk_bytes = a.cout * 128;
@@ -449,7 +448,8 @@ struct ApplyShape {
   int nb_slots, passes, a_stages, smem_bytes;
 };
 
-bool apply_shape(int cout, int Kp, ApplyShape* as) {
+bool apply_shape(int cout, int Kp, int ybn, ApplyShape* as) {
+  const int kYStageBytes = kATileBytes + ybn * 64 * 2;
   if (cout % 16 != 0 || cout < 16 || 2 * kTU * cout > 256 || Kp % 64 != 0) return false;
   const int num_kc = Kp / 64;
   const int b_stride = (cout * 128 + 1023) & ~1023;
@@ -478,11 +478,18 @@ bool apply_shape(int cout, int Kp, ApplyShape* as) {
 
 }  // namespace
 
+static int y_block_n() {
+  // N tile of the Y pipeline: 64 (default: smaller stage -> 7 instead of 6 A stages for the h stream, measured
+  // 72.6 vs 74.1 ms per step at 241^2, run27) or 128
+  if (const char* e = getenv("NNCONV_Y_BLOCKN")) return atoi(e) == 128 ? 128 : 64;
+  return 64;
+}
+
 bool apply_fused_supported(const Weights* W) {
   if (W->prec != PREC_F16 && W->prec != PREC_BF16) return false;
-  if ((W->cout * W->Kp) % kYBlockN != 0) return false;
+  if ((W->cout * W->Kp) % 128 != 0) return false;
   ApplyShape as;
-  return apply_shape(W->cout, W->Kp, &as);
+  return apply_shape(W->cout, W->Kp, y_block_n(), &as);
 }
 
 int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, const void* Xc, void* Yring, int nb,
@@ -491,8 +498,10 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
   int s = tc_init();
   if (s != NNCONV_OK) return s;
   const int bf = prec == PREC_BF16;
+  const int ybn = y_block_n();
   ApplyShape as;
-  NNC_REQUIRE(apply_shape(W->cout, W->Kp, &as), NNCONV_ERR_UNSUPPORTED, "apply_tc: unsupported shape");
+  NNC_REQUIRE(apply_shape(W->cout, W->Kp, ybn, &as), NNCONV_ERR_UNSUPPORTED, "apply_tc: unsupported shape");
+  if (const char* e = getenv("NNCONV_APPLY_STAGES")) { int v = atoi(e); if (v >= 2 && v < as.a_stages) as.a_stages = v; }
   const int64_t e_pad = round_up64(P->E, 128);
   const int NY = W->cout * W->Kp;
   const int n_batches = ceil_div(P->n_src, nb);
@@ -507,7 +516,7 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
   if (s != NNCONV_OK) return s;
   s = make_tmap_2d_16b(&tmX, bf, Xc, static_cast<uint64_t>(P->n_src), static_cast<uint64_t>(W->cin_p), 128);
   if (s != NNCONV_OK) return s;
-  s = make_tmap_2d_16b(&tmW, bf, W->W3p, static_cast<uint64_t>(NY), static_cast<uint64_t>(W->cin_p), kYBlockN);
+  s = make_tmap_2d_16b(&tmW, bf, W->W3p, static_cast<uint64_t>(NY), static_cast<uint64_t>(W->cin_p), ybn);
   if (s != NNCONV_OK) return s;
   ApplyArgs a;
   a.tile_c = P->tile_c; a.tile_e0 = P->tile_e0; a.tile_cnt = P->tile_cnt; a.tile_ptr = P->tile_ptr;
@@ -525,11 +534,13 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
     TraceHandle th = trace_get();
     a.trace = TraceBuf{th.rec, th.count, th.cap};
   }
-  static int attr_set[2] = {0, 0};
-  if (!attr_set[bf]) {
-    if (bf) NNC_CHECK_CUDA(cudaFuncSetAttribute(k_apply_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    else NNC_CHECK_CUDA(cudaFuncSetAttribute(k_apply_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set[bf] = 1;
+  static int attr_set = 0;
+  if (!attr_set) {
+    NNC_CHECK_CUDA(cudaFuncSetAttribute(k_apply_tc<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    NNC_CHECK_CUDA(cudaFuncSetAttribute(k_apply_tc<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    NNC_CHECK_CUDA(cudaFuncSetAttribute(k_apply_tc<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    NNC_CHECK_CUDA(cudaFuncSetAttribute(k_apply_tc<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = 1;
   }
   // Optional (NNCONV_L2_PERSIST=1): pin the Y ring in L2 with an access-policy window on the caller's stream
   // for the duration of this launch (persisting hits for the ring, everything else streaming).
@@ -559,8 +570,13 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
   }
   // every CTA must be resident (the flags couple all CTAs): exactly one CTA per SM, never more than #SMs
   const int grid = tc_num_sms();
-  if (bf) k_apply_tc<1><<<grid, kThreads, as.smem_bytes, st>>>(tmH, tmY, tmX, tmW, a);
-  else k_apply_tc<0><<<grid, kThreads, as.smem_bytes, st>>>(tmH, tmY, tmX, tmW, a);
+  if (ybn == 64) {
+    if (bf) k_apply_tc<1, 64><<<grid, kThreads, as.smem_bytes, st>>>(tmH, tmY, tmX, tmW, a);
+    else k_apply_tc<0, 64><<<grid, kThreads, as.smem_bytes, st>>>(tmH, tmY, tmX, tmW, a);
+  } else {
+    if (bf) k_apply_tc<1, 128><<<grid, kThreads, as.smem_bytes, st>>>(tmH, tmY, tmX, tmW, a);
+    else k_apply_tc<0, 128><<<grid, kThreads, as.smem_bytes, st>>>(tmH, tmY, tmX, tmW, a);
+  }
   if (window_set) {
     cudaStreamAttrValue v{};
     v.accessPolicyWindow.num_bytes = 0;
