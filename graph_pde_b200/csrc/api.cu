@@ -152,13 +152,23 @@ static int max_hidden_kp(const Weights* W) {
   return m;
 }
 
+// How the first two layers run: 0 = two GEMM kernels (h1 through HBM), 1 = on-chip fusion (mlp_fused_tc.cu,
+// experimental), 2 = two pipelines meeting in an L2 ring (mlp_ring_tc.cu).  NNCONV_MLP12 = split | onchip | ring.
+static int ef_mlp12_mode(const Weights* W) {
+  if (W->W1aug == nullptr || W->n_layers < 3) return 0;
+  const char* e = getenv("NNCONV_MLP12");
+  if (e != nullptr) {
+    if (strcmp(e, "ring") == 0) return 2;
+    if (strcmp(e, "onchip") == 0) return 1;
+    if (strcmp(e, "split") == 0) return 0;
+  }
+  const char* f = getenv("NNCONV_FUSE12");
+  if (f != nullptr && atoi(f) > 0) return 1;
+  return 0;
+}
+
 static bool ef_fuse12(const Weights* W) {
-  // first two layers in one kernel (mlp_fused_tc.cu).  EXPERIMENTAL, off by default (NNCONV_FUSE12=1): every
-  // variant measured this round (profiles/r1e_*) was slower than the two separate GEMMs -- routing the fp32
-  // first-layer accumulator through TMEM costs a 32 KB tcgen05.ld per 64-column block, about the whole
-  // 576-cycle budget of that block at the measured TMEM read rate.
-  const char* e = getenv("NNCONV_FUSE12");
-  return W->W1aug != nullptr && W->n_layers >= 3 && e != nullptr && atoi(e) > 0;
+  return ef_mlp12_mode(W) != 0;
 }
 
 static size_t ef_row_bytes(const Weights* W) {
@@ -178,7 +188,9 @@ size_t edge_features_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes
   rows = rows / 128 * 128;
   if (rows < 128) rows = 128;
   if (rows > rows_all) rows = rows_all;
-  return rows * row + 4096;
+  size_t ring = 0;
+  if (ef_mlp12_mode(W) == 2) ring = static_cast<size_t>(round_up64(static_cast<int64_t>(mlp_ring_bytes(W->kp[1])), 1024));
+  return ring + rows * row + 8192;
 }
 
 int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void* h, void* ws, size_t ws_bytes,
@@ -205,10 +217,21 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
     if (launches) ++*launches;
     return s;
   }
+  const int mlp12 = ef_mlp12_mode(W);
+  const bool fuse12 = mlp12 != 0;
+  size_t ring_bytes = 0;
+  char* ring = nullptr;
+  if (mlp12 == 2) {    // the per-CTA h1 ring sits at the start of the workspace
+    ring_bytes = static_cast<size_t>(round_up64(static_cast<int64_t>(mlp_ring_bytes(W->kp[1])), 1024));
+    NNC_REQUIRE(ws != nullptr && ws_bytes > ring_bytes + 128 * rowb + 4096, NNCONV_ERR_WORKSPACE,
+                "edge_features: workspace too small for the h1 ring");
+    ring = static_cast<char*>(ws);
+    ws = ring + ring_bytes;
+    ws_bytes -= ring_bytes;
+  }
   NNC_REQUIRE(ws != nullptr && ws_bytes >= 128 * rowb + 4096, NNCONV_ERR_WORKSPACE, "edge_features: workspace too small");
   const int64_t rows = static_cast<int64_t>((ws_bytes - 4096) / rowb) / 128 * 128;
   const size_t hid = static_cast<size_t>(max_hidden_kp(W)) * W->esize;
-  const bool fuse12 = ef_fuse12(W);
   char* a1 = static_cast<char*>(ws);
   char* bufA = a1 + (W->W1aug ? round_up64(rows * 128, 1024) : 0);
   char* bufB = bufA + round_up64(static_cast<int64_t>(rows * hid), 1024);
@@ -227,8 +250,12 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
       const bool last2 = nl == 3;
       {
         ProfScope ps(PK_HIDDEN_GEMM, st);
-        s = launch_mlp12_tc(W->prec, a1, n, W->dims[0], W->W1aug, W->kp[1], W->Wh[2], W->kp[2], W->bh[2],
-                            last2 ? h_rows : static_cast<void*>(bufA), W->kp[2], last2 ? hpad : 0, e0, st);
+        if (mlp12 == 2)
+          s = launch_mlp_ring_tc(W->prec, a1, n, W->dims[0], W->W1aug, W->kp[1], W->Wh[2], W->kp[2], W->bh[2], ring,
+                                 last2 ? h_rows : static_cast<void*>(bufA), W->kp[2], last2 ? hpad : 0, e0, st);
+        else
+          s = launch_mlp12_tc(W->prec, a1, n, W->dims[0], W->W1aug, W->kp[1], W->Wh[2], W->kp[2], W->bh[2],
+                              last2 ? h_rows : static_cast<void*>(bufA), W->kp[2], last2 ? hpad : 0, e0, st);
       }
       if (s) return s;
       if (launches) *launches += 2;

@@ -60,6 +60,12 @@ int launch_mlp12_tc(int prec, const void* A1, int64_t rows, int k_in, const void
                     int N, const float* bias2, void* C, int64_t ldc, int64_t chunk_rows_pad, int64_t c_row0,
                     cudaStream_t st);
 
+// ---- mlp_ring_tc.cu: first two MLP layers as two pipelines per CTA meeting in an L2-resident ring
+size_t mlp_ring_bytes(int K1p);
+int launch_mlp_ring_tc(int prec, const void* A1, int64_t rows, int k_in, const void* W1aug, int K1p, const void* W2,
+                       int N, const float* bias2, void* ring, void* C, int64_t ldc, int64_t chunk_rows_pad,
+                       int64_t c_row0, cudaStream_t st);
+
 // ---- apply_tc.cu: ONE persistent kernel per application (Y GEMM + contraction pipelines in every CTA)
 bool apply_fused_supported(const Weights* W);
 int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, const void* Xc, void* Yring, int nb,

@@ -167,7 +167,7 @@ def test_properties_at_config2_size(dev):
     assert rel_err(o_mean, o_add / deg[:, None]) < 1e-5
 
 
-@pytest.mark.parametrize('knob', ['NNCONV_NO_FUSE', 'NNCONV_NO_PIPE+NNCONV_NO_FUSE', 'NNCONV_RING=4', 'small_ring', 'NNCONV_FUSE12=1'])
+@pytest.mark.parametrize('knob', ['NNCONV_NO_FUSE', 'NNCONV_NO_PIPE+NNCONV_NO_FUSE', 'NNCONV_RING=4', 'small_ring', 'NNCONV_FUSE12=1', 'NNCONV_MLP12=ring'])
 def test_alternative_schedules_give_the_same_answer(dev, knob, monkeypatch):
     """The fused persistent kernel (default), the per-batch PDL-pipelined kernels (NNCONV_NO_FUSE) and the
     plain stream-ordered kernels (NNCONV_NO_PIPE) must agree; a tiny Y ring forces many batches through the
