@@ -151,6 +151,43 @@ def cpu_reference_rate(cfg, seconds_target, steps=1, warmup=0):
     return ei.size(1) * T * len(times) / tot, cores, desc, 1e3 * tot / len(times)
 
 
+def gpu_reference_rate(cfg, dev, n_src=2048, chunk=65536):
+    """the reference-equivalent PyTorch path (the oracle port, fp32, allow_tf32=False, scatter =
+    index_add_) on CUDA tensors, edge-chunked, on a bounded sample -- the 'reference single-GPU path' the north
+    star's >= 10x refers to.  CUDA-event timing.  Baseline only; never part of the product path."""
+    from graph_pde_b200 import graphs
+    from oracle import nnconv_oracle as O
+    s, r, w, kw, T = cfg['s'], cfg['r'], cfg['width'], cfg['ker_width'], cfg['depth']
+    n = s * s
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ws, bs, root, bias = O.reference_init(w, w, [6, kw, kw, w * w], seed=0)
+        ws, bs, root, bias = [t.to(dev) for t in ws], [t.to(dev) for t in bs], root.to(dev), bias.to(dev)
+        n_src = min(n, n_src)
+        ei = graphs.ball_connectivity(s, r, dev, True, nodes=(0, n_src))
+        grid = graphs.square_grid(s, dev)
+        ea = graphs.ball_edge_attr(grid, ei, torch.randn(n, device=dev))
+        x = torch.randn(n, w, device=dev)
+
+        def run():
+            with torch.no_grad():
+                O.kernelnn_conv_stack(x, ei, ea, ws, bs, root, bias, T, 'mean', edge_chunk=chunk)
+        run()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        run()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    return dict(value=ei.size(1) * T / (ms * 1e-3), unit='edge-apps/s', kind='port-on-cuda',
+                sample='out-edges of the first %d source nodes (%d edges) x T=%d, fp32 torch ops (allow_tf32=False), '
+                       'edge_chunk %d, one timed pass after one warm-up' % (n_src, ei.size(1), T, chunk))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -349,6 +386,7 @@ def main():
                                               % (f_alg, b_alg)),
                     edges=E, nodes=N)
         if not args.no_cpu_baseline:
+            line['gpu_reference_port'] = gpu_reference_rate(cfg, dev)
             rate, cores, desc, _ = cpu_reference_rate(cfg, 12.0)
             line['cpu_baseline'] = dict(value=rate, unit='edge-apps/s', cores=cores, kind='port', sample=desc)
         print(json.dumps(line))

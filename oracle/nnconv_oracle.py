@@ -2,9 +2,10 @@
 
 A CPU restatement (torch-CPU / numpy, fp32 or fp64) of the reference algorithm, each function citing
 the reference file:line it follows (paths relative to /root/reference, GNO = graph-neural-operator,
-MGNO = multipole-graph-neural-operator).  Only tests/, __graft_entry__.smoke() and bench.py's
-cpu_baseline / --impl reference legs may import this module; the product path (graph_pde_b200) never
-does and fails loudly when its CUDA library is missing.
+MGNO = multipole-graph-neural-operator).  Only tests/, __graft_entry__.smoke() and bench.py's baseline
+legs (cpu_baseline, --impl reference, and gpu_reference_port = these same torch ops on CUDA tensors, the
+"reference single-GPU path" of SURVEY 8(d)(ii)) may import this module; the product path (graph_pde_b200)
+never does and fails loudly when its CUDA library is missing.
 
 Pinning: this restatement is checked (tests/test_oracle_golden.py) against golden vectors produced by
 running the reference's own nn_conv.py / utilities.py UNMODIFIED in the build container
@@ -55,7 +56,7 @@ def nnconv_forward(x, edge_index, edge_attr, weights, biases, root=None, bias=No
     cout = (weights[-1].size(0) // cin) if out_channels is None else out_channels
     src, dst = edge_index[0], edge_index[1]
     e_total = src.numel()
-    out = torch.zeros(n, cout, dtype=x.dtype)
+    out = torch.zeros(n, cout, dtype=x.dtype, device=x.device)
     step = e_total if (edge_chunk is None or edge_chunk <= 0) else edge_chunk
     for s in range(0, max(e_total, 1), max(step, 1)):
         sl = slice(s, min(s + step, e_total))
@@ -66,8 +67,8 @@ def nnconv_forward(x, edge_index, edge_attr, weights, biases, root=None, bias=No
         msg = torch.matmul(x_j.unsqueeze(1), w).squeeze(1)              # nn_conv.py:275
         out.index_add_(0, dst[sl], msg)                                # PyG scatter_('add'|'mean')
     if aggr == 'mean':
-        cnt = torch.zeros(n, dtype=x.dtype)
-        cnt.index_add_(0, dst, torch.ones(e_total, dtype=x.dtype))
+        cnt = torch.zeros(n, dtype=x.dtype, device=x.device)
+        cnt.index_add_(0, dst, torch.ones(e_total, dtype=x.dtype, device=x.device))
         out = out / cnt.clamp(min=1).unsqueeze(-1)
     elif aggr != 'add':
         raise ValueError('oracle supports aggr in {add, mean}')
