@@ -74,3 +74,75 @@ def darcy_sample(s, r, device='cpu', seed=0, edge_index=None, ties_in=True):
     x = torch.cat([grid, feats], dim=1).contiguous()
     edge_attr = ball_edge_attr(grid, edge_index, feats[:, 0])
     return x, edge_index, edge_attr
+
+
+# ------------------------------------------------------------------------------------------------------
+# Multi-level (MGKN) graphs: RandomMultiMeshGenerator restated (multipole-graph-neural-operator/
+# utilities.py:546-712) with torch ops on any device.
+# ------------------------------------------------------------------------------------------------------
+def _ball_pairs(pa, pb, radius):
+    """np.vstack(np.where(pairwise_distances(pa, pb) <= radius)): row-major order = source-major, dst ascending.
+    Float64 distances; lattice ties with `radius` are rounding-dependent in the reference too."""
+    d = torch.cdist(pa.double(), pb.double())
+    idx = torch.nonzero(d <= radius, as_tuple=False)
+    return idx.t().contiguous()
+
+
+class MultiLevelGraph(object):
+    """Output of ``multi_level_ball_graph`` with the field names the MGKN scripts put on their ``Data``
+    (neurips1_MGKN.py:208-224): edge_index_{mid,down,up} (concatenated over levels, global node ids),
+    edge_index_range / _down_range / _up_range ([L,2] / [L-1,2]), edge_attr_{mid,down,up}, sample_idx."""
+    pass
+
+
+def multi_level_ball_graph(s, sample_sizes, radius_inner, radius_inter, theta=None, device='cpu', generator=None):
+    """sample(): one torch.randperm(s*s) split into consecutive level chunks (utilities.py:581-593);
+    ball_connectivity(): per-level ball graphs offset by the level's first node id, inter-level bipartite graphs
+    level l -> l+1 ("down") and their transposes ("up") (:602-643); attributes(): [pos_src, pos_dst,
+    theta_src, theta_dst] (:672-706).  theta: [s*s] tensor or None (then edge_attr has 4 columns)."""
+    level = len(sample_sizes)
+    assert len(radius_inner) == level and len(radius_inter) == level - 1
+    grid = square_grid(s, 'cpu', torch.float64)
+    perm = torch.randperm(s * s, generator=generator)
+    idx, pos, start = [], [], [0]
+    off = 0
+    for m in sample_sizes:
+        idx.append(perm[off:off + m])
+        pos.append(grid[idx[-1]].to(device))
+        off += m
+        start.append(off)
+    idx_all = perm[:off]
+    pos_all = grid[idx_all].to(device)
+    mid, down, up = [], [], []
+    for l in range(level):
+        mid.append(_ball_pairs(pos[l], pos[l], radius_inner[l]) + start[l])
+    for l in range(level - 1):
+        e = _ball_pairs(pos[l], pos[l + 1], radius_inter[l])
+        e = torch.stack([e[0] + start[l], e[1] + start[l + 1]])
+        down.append(e)
+        up.append(e[[1, 0], :])
+
+    def ranges(parts):
+        r, n = [], 0
+        for p in parts:
+            r.append([n, n + p.size(1)])
+            n += p.size(1)
+        return torch.tensor(r, dtype=torch.long)
+
+    def attrs(e):
+        cols = [pos_all[e[0]], pos_all[e[1]]]
+        if theta is not None:
+            th = theta.to(device).double()[idx_all.to(device)]
+            cols += [th[e[0], None], th[e[1], None]]
+        return torch.cat(cols, dim=1).float().contiguous()
+
+    g = MultiLevelGraph()
+    g.sample_idx = idx_all
+    g.points = list(sample_sizes)
+    g.pos = pos_all.float()
+    g.edge_index_mid = torch.cat(mid, dim=1)
+    g.edge_index_down = torch.cat(down, dim=1)
+    g.edge_index_up = torch.cat(up, dim=1)
+    g.edge_index_range, g.edge_index_down_range, g.edge_index_up_range = ranges(mid), ranges(down), ranges(up)
+    g.edge_attr_mid, g.edge_attr_down, g.edge_attr_up = attrs(g.edge_index_mid), attrs(g.edge_index_down), attrs(g.edge_index_up)
+    return g

@@ -232,6 +232,20 @@ def main():
         rec['ei/%d_%g' % (s, r)] = ei.numpy().astype(np.int32)
         rec['ea/%d_%g' % (s, r)] = mg.attributes(theta=th).numpy()
     np.savez_compressed(os.path.join(OUT, 'g6_ball_graphs.npz'), **rec)
+    # ---------------- G7: multi-level (MGKN) graph generator pins, RandomMultiMeshGenerator, seeded ----------
+    s, m, ri, rx = 31, [200, 80, 30], [0.155, 0.31, 0.62], [0.21, 0.41]    # radii without lattice ties
+    torch.manual_seed(0)
+    mmg = MU.RandomMultiMeshGenerator([[0, 1], [0, 1]], [s, s], level=3, sample_sizes=m)
+    mmg.sample()
+    e_mid, e_down, e_up = mmg.ball_connectivity(ri, rx)
+    r_mid, r_down, r_up = mmg.get_edge_index_range()
+    theta = np.random.RandomState(0).randn(s * s)
+    a_mid, a_down, a_up = mmg.attributes(theta=theta)
+    np.savez_compressed(os.path.join(OUT, 'g7_multilevel_graph.npz'), s=s, m=np.array(m), ri=np.array(ri),
+                        rx=np.array(rx), theta=theta, e_mid=e_mid.numpy().astype(np.int32),
+                        e_down=e_down.numpy().astype(np.int32), e_up=e_up.numpy().astype(np.int32),
+                        r_mid=r_mid.numpy(), r_down=r_down.numpy(), r_up=r_up.numpy(),
+                        a_mid=a_mid.numpy(), a_down=a_down.numpy(), a_up=a_up.numpy())
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -113,6 +113,21 @@ def test_graph_builder_matches_oracle_and_sklearn_golden():
     assert full.size(1) == 25673                                # ties-in rule
 
 
+def test_multilevel_graph_builder_matches_reference_golden():
+    """graphs.multi_level_ball_graph vs RandomMultiMeshGenerator (multipole-graph-neural-operator/
+    utilities.py:546-712) on the seeded G7 fixture: same randperm stream, same edge order, ranges and attributes."""
+    g7 = np.load(os.path.join(GOLDEN, 'g7_multilevel_graph.npz'))
+    torch.manual_seed(0)
+    g = graphs.multi_level_ball_graph(int(g7['s']), [int(v) for v in g7['m']], list(g7['ri']), list(g7['rx']),
+                                      theta=torch.from_numpy(g7['theta']))
+    for name, key in (('edge_index_mid', 'e_mid'), ('edge_index_down', 'e_down'), ('edge_index_up', 'e_up'),
+                      ('edge_index_range', 'r_mid'), ('edge_index_down_range', 'r_down'),
+                      ('edge_index_up_range', 'r_up')):
+        assert np.array_equal(getattr(g, name).numpy(), g7[key].astype(np.int64)), name
+    for name, key in (('edge_attr_mid', 'a_mid'), ('edge_attr_down', 'a_down'), ('edge_attr_up', 'a_up')):
+        assert np.allclose(getattr(g, name).numpy(), g7[key], atol=1e-6), name
+
+
 def test_dropin_modules_resolve_like_the_reference_imports(monkeypatch):
     import importlib
     import sys
