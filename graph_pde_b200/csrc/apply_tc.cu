@@ -62,6 +62,7 @@ struct ApplyArgs {
   int* okC;
   int* cntU;              // units handed out so far (one counter per application)
   unsigned long long y_store_policy;   // L2 eviction-priority hint of the Y ring stores
+  int debug_scatter;      // timing experiments only (NNCONV_DEBUG_SCATTER): 1 = drop the scatter, 2 = plain stores
   TraceBuf trace;
 };
 
@@ -301,7 +302,13 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
             uint32_t v[16];
             tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * kTU + ti) * a.cout + cc, v);
             tmem_ld_wait();
-            if (ok[ti]) {
+            if (ok[ti] && a.debug_scatter == 2) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(orow + cc + 4 * q) =
+                    make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                                __uint_as_float(v[4 * q + 3]));
+            } else if (ok[ti] && a.debug_scatter == 0) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const float4 cq = __ldg(reinterpret_cast<const float4*>(cv + cc) + q);
@@ -384,8 +391,10 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
       const int tiles = ((rows + 127) / 128) * n_blocks;
       const unsigned long long ty0 = a.trace.rec ? gtime() : 0ull;
       if (b >= a.ring) {                         // the ring slot must have been consumed by every CTA
-        if (lane == 0) flag_wait(a.okC + (b - a.ring));
-        __syncwarp();
+        // ONE slow poller per CTA (the Y pipeline runs ring-1 batches ahead, so this wait is long -- 20-35 us per
+        // batch -- and never urgent); the other three epilogue warps park on a named barrier
+        if (warp == 8 && lane == 0) flag_wait(a.okC + (b - a.ring), 500);
+        named_bar_sync(2, 128);
       }
       const unsigned long long ty1 = a.trace.rec ? gtime() : 0ull;
       uint16_t* ybase = reinterpret_cast<uint16_t*>(a.Yring) + static_cast<int64_t>(b % a.ring) * a.nb * a.NY;
@@ -527,6 +536,8 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
   a.e_pad = static_cast<int>(e_pad);
   a.NY = NY; a.num_kx = W->cin_p / 64; a.Yring = Yring;
   a.y_store_policy = kEvictNormal;
+  a.debug_scatter = 0;
+  if (const char* e = getenv("NNCONV_DEBUG_SCATTER")) a.debug_scatter = atoi(e);   // wrong results, timing only
   if (const char* e = getenv("NNCONV_Y_STORE_POLICY")) a.y_store_policy = atoi(e) == 1 ? kEvictLast : atoi(e) == 2 ? kEvictFirst : kEvictNormal;
   a.cntY = flags; a.cntC = flags + flags_stride; a.okY = flags + 2 * flags_stride; a.okC = flags + 3 * flags_stride;
   a.cntU = flags + 4 * flags_stride;

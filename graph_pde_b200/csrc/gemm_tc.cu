@@ -6,7 +6,7 @@
 //
 // Structure: persistent CTAs (grid = #SMs), 10 warps: warp 0 = TMA producer (one lane), warp 1 = MMA
 // issuer (one lane) + TMEM allocator, warps 2..9 = epilogue (TMEM -> registers -> bias/ReLU -> 16-bit
-// -> global).  Operands are K-major 128B-swizzled tiles [128 x 64] / [BLOCK_N x 64] staged by TMA in a
+// -> per-warp swizzled smem piece -> TMA store; direct 32-byte stores for pipelined / small launches).  Operands are K-major 128B-swizzled tiles [128 x 64] / [BLOCK_N x 64] staged by TMA in a
 // ring of kStages; accumulators are double buffered in TMEM (2 x BLOCK_N columns) so the epilogue of
 // tile i overlaps the MMAs of tile i+1.
 #include "kernels.h"
@@ -35,6 +35,12 @@ struct GemmTcArgs {
   const int* wait_ok;
   int* done_cnt;
   int* done_ok;
+  // 1: every epilogue warp stages its [32 rows x 32 cols] piece in its own double-buffered 2 KB of shared
+  // memory (64-byte swizzle) and lane 0 writes it with TMA (tmC): no global stores on the LSU data pipe, which
+  // ncu r1f showed at 85% in the K = 64 first-layer GEMM (TMEM loads + stores touching 32 lines per instruction),
+  // no block-level barrier, and the store of piece i drains while piece i+1 is converted.
+  int tma_store;
+  int bias_v4;         // bias is 16-byte aligned: float4 loads
   TraceBuf trace;
   unsigned int trace_seq;
 };
@@ -51,19 +57,23 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = SMALL ? 3 : ((196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes));
   static constexpr int kTmemCols = 2 * BLOCK_N;   // power of two >= 32 for BLOCK_N in {64,128,256}
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  // output staging for the TMA-store epilogue: 8 warps x 2 buffers x [32 x 32] 16-bit pieces
+  static constexpr int kStoreBytes = SMALL ? 0 : 8 * 2 * 2048;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BLOCK_N, int FMT, int SMALL>
 __global__ void __launch_bounds__(320, SMALL ? 2 : 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmTcArgs a) {
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ CUtensorMap tmC, GemmTcArgs a) {
   using Cfg = GemmCfg<BLOCK_N, SMALL>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + Cfg::kStages * Cfg::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* smem_c = smem + Cfg::kStages * Cfg::kStageBytes;     // 1024-aligned (stage sizes are multiples of 8 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + Cfg::kStoreBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::kStages;
   uint64_t* tfull = bars + 2 * Cfg::kStages;
@@ -79,6 +89,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (a.tma_store) prefetch_tmap(&tmC);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -157,6 +168,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int half = (warp - 2) / 4;  // which half of the BLOCK_N columns
     constexpr int kChunks = BLOCK_N / 64;          // 32-column chunks per half
     int it = 0;
+    uint32_t piece = 0;   // TMA-store pieces issued by this warp (selects the staging buffer)
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int mb = t / n_blocks, nb = t % n_blocks;
       const int as = it & 1;
@@ -171,38 +183,74 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       uint32_t v[2][32];
       tmem_ld32(tbase, v[0]);
       tmem_ld_wait();
+      const bool use_tma = Cfg::kStoreBytes > 0 && a.tma_store != 0;
+      // this warp's staging: 2 buffers of 32 rows x 64 B; 16-byte unit u of row r sits at (u ^ ((r >> 1) & 3))
+      // (SWIZZLE_64B of tmC) -- conflict-free for the 8-lane phases of a v4 shared store
+      const uint32_t stage0 = smem_u32(smem_c) + (warp - 2) * 4096;
+      const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
 #pragma unroll
       for (int cc = 0; cc < kChunks; ++cc) {
         if (cc + 1 < kChunks) tmem_ld32(tbase + (cc + 1) * 32, v[(cc + 1) & 1]);
         const int col0 = nb * BLOCK_N + half * (BLOCK_N / 2) + cc * 32;
-        if (col0 < a.N && row_ok) {
+        if (col0 < a.N && (row_ok || use_tma)) {
           const uint32_t* vv = v[cc & 1];
           uint32_t packed[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float f0 = __uint_as_float(vv[2 * j]), f1 = __uint_as_float(vv[2 * j + 1]);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float f[4] = {__uint_as_float(vv[4 * j4]), __uint_as_float(vv[4 * j4 + 1]),
+                          __uint_as_float(vv[4 * j4 + 2]), __uint_as_float(vv[4 * j4 + 3])};
             if (a.bias) {
-              f0 += __ldg(a.bias + col0 + 2 * j);
-              f1 += __ldg(a.bias + col0 + 2 * j + 1);
+              if (a.bias_v4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + col0) + j4);
+                f[0] += b4.x; f[1] += b4.y; f[2] += b4.z; f[3] += b4.w;
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) f[q] += __ldg(a.bias + col0 + 4 * j4 + q);
+              }
             }
             if (a.relu) {
-              f0 = fmaxf(f0, 0.f);
-              f1 = fmaxf(f1, 0.f);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) f[q] = fmaxf(f[q], 0.f);
             }
-            if (FMT == 0) {
-              __half2 h = __floats2half2_rn(f0, f1);
-              packed[j] = *reinterpret_cast<uint32_t*>(&h);
-            } else {
-              __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-              packed[j] = *reinterpret_cast<uint32_t*>(&h);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              if (FMT == 0) {
+                __half2 h = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
+                packed[2 * j4 + q] = *reinterpret_cast<uint32_t*>(&h);
+              } else {
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+                packed[2 * j4 + q] = *reinterpret_cast<uint32_t*>(&h);
+              }
             }
           }
-          uint16_t* dst = a.chunk_rows_pad > 0
-                              ? reinterpret_cast<uint16_t*>(a.C) +
-                                    (static_cast<int64_t>(col0 >> 6) * a.chunk_rows_pad + grow) * 64 + (col0 & 63)
-                              : crow + col0;
-          st_global_v8(dst, packed);            // 2 x 32 B: full sectors (16 B stores were half-used
-          st_global_v8(dst + 16, packed + 8);   // sectors, ncu r1a)
+          if (use_tma) {
+            const uint32_t buf = stage0 + (piece & 1) * 2048;
+            if (lane == 0) bulk_wait_read1();                 // the store issued two pieces ago has left this buffer
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              st_shared_v4(buf + lane * 64 + ((static_cast<uint32_t>(u) ^ sw) << 4), packed[4 * u], packed[4 * u + 1],
+                           packed[4 * u + 2], packed[4 * u + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int r0 = mb * Cfg::kBlockM + quarter * 32;
+              if (a.chunk_rows_pad > 0)
+                tma_store_2d(&tmC, buf, col0 & 63,
+                             static_cast<int>((col0 >> 6) * a.chunk_rows_pad + a.c_row0 + r0));
+              else
+                tma_store_2d(&tmC, buf, col0, r0);
+              bulk_commit();
+            }
+            ++piece;
+          } else {
+            uint16_t* dst = a.chunk_rows_pad > 0
+                                ? reinterpret_cast<uint16_t*>(a.C) +
+                                      (static_cast<int64_t>(col0 >> 6) * a.chunk_rows_pad + grow) * 64 + (col0 & 63)
+                                : crow + col0;
+            st_global_v8(dst, packed);            // 2 x 32 B: full sectors (16 B stores were half-used
+            st_global_v8(dst + 16, packed + 8);   // sectors, ncu r1a)
+          }
         }
         if (cc + 1 < kChunks) tmem_ld_wait();
       }
@@ -211,6 +259,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (lane == 0) mbar_arrive(&tempty[as]);
     }
   }
+  if (Cfg::kStoreBytes > 0 && a.tma_store && warp >= 2 && lane == 0) bulk_wait0();
   fence_before_sync();
   if (a.done_cnt != nullptr) signal_done(a.done_cnt, a.done_ok);   // includes __syncthreads
   else __syncthreads();
@@ -224,7 +273,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 int g_num_sms = 0;
 
 template <int BLOCK_N, int FMT, int SMALL>
-int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTcArgs& a, cudaStream_t st, bool pdl) {
+int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmTcArgs& a,
+                    cudaStream_t st, bool pdl) {
   using Cfg = GemmCfg<BLOCK_N, SMALL>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -245,7 +295,7 @@ int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmTc
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  NNC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<BLOCK_N, FMT, SMALL>, tmA, tmB, a));
+  NNC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<BLOCK_N, FMT, SMALL>, tmA, tmB, tmC, a));
   return NNCONV_OK;
 }
 
@@ -295,14 +345,33 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
     a.trace = TraceBuf{th.rec, th.count, th.cap};
     a.trace_seq = launch_seq++;
   }
+  // TMA-store epilogue: [32 x 32] pieces; rows past M are clipped by the tensor bounds (row-major) or land in
+  // the row padding of each chunk panel (chunk-major, chunk_rows_pad >= round_up(c_row0 + M, 32))
+  static const bool no_tma_store = getenv("NNCONV_GEMM_DIRECT_STORE") != nullptr;
+  a.tma_store = 0;
+  a.bias_v4 = bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
+  CUtensorMap tmC = tmA;
+  const bool panel_ok = chunk_rows_pad > 0
+                            ? ((c_row0 + M + 31) / 32 * 32 <= chunk_rows_pad &&
+                               static_cast<int64_t>(N / 64) * chunk_rows_pad < (int64_t(1) << 31))
+                            : ldc == N;
+  if (!no_tma_store && pf == nullptr && panel_ok) {
+    if (chunk_rows_pad > 0) {
+      s = make_tmap_store_16b(&tmC, bf, C, static_cast<uint64_t>(N / 64) * static_cast<uint64_t>(chunk_rows_pad), 64);
+    } else {
+      s = make_tmap_store_16b(&tmC, bf, C, static_cast<uint64_t>(M), static_cast<uint64_t>(N));
+    }
+    if (s != NNCONV_OK) return s;
+    a.tma_store = 1;
+  }
   a.wait_ok = pf ? pf->wait_ok : nullptr;
   a.done_cnt = pf ? pf->done_cnt : nullptr;
   a.done_ok = pf ? pf->done_ok : nullptr;
   const bool pdl = pf && pf->pdl;
-  if (small) return bf ? launch_gemm_cfg<128, 1, 1>(tmA, tmB, a, st, pdl) : launch_gemm_cfg<128, 0, 1>(tmA, tmB, a, st, pdl);
-  if (BN == 256) return bf ? launch_gemm_cfg<256, 1, 0>(tmA, tmB, a, st, pdl) : launch_gemm_cfg<256, 0, 0>(tmA, tmB, a, st, pdl);
-  if (BN == 128) return bf ? launch_gemm_cfg<128, 1, 0>(tmA, tmB, a, st, pdl) : launch_gemm_cfg<128, 0, 0>(tmA, tmB, a, st, pdl);
-  return bf ? launch_gemm_cfg<64, 1, 0>(tmA, tmB, a, st, pdl) : launch_gemm_cfg<64, 0, 0>(tmA, tmB, a, st, pdl);
+  if (small) return bf ? launch_gemm_cfg<128, 1, 1>(tmA, tmB, tmC, a, st, pdl) : launch_gemm_cfg<128, 0, 1>(tmA, tmB, tmC, a, st, pdl);
+  if (BN == 256) return bf ? launch_gemm_cfg<256, 1, 0>(tmA, tmB, tmC, a, st, pdl) : launch_gemm_cfg<256, 0, 0>(tmA, tmB, tmC, a, st, pdl);
+  if (BN == 128) return bf ? launch_gemm_cfg<128, 1, 0>(tmA, tmB, tmC, a, st, pdl) : launch_gemm_cfg<128, 0, 0>(tmA, tmB, tmC, a, st, pdl);
+  return bf ? launch_gemm_cfg<64, 1, 0>(tmA, tmB, tmC, a, st, pdl) : launch_gemm_cfg<64, 0, 0>(tmA, tmB, tmC, a, st, pdl);
 }
 
 }  // namespace nnc

@@ -69,6 +69,27 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// 2-D tile store smem -> global through the async proxy (bulk group completion).  The smem tile uses the tensor
+// map's swizzle; rows/columns outside the tensor are clipped by the hardware.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(m), "r"(smem_src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed groups have finished READING shared memory (the buffer may be overwritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recent one
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// all committed groups are complete (global writes performed)
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
@@ -182,7 +203,10 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   return v;
 }
 // one thread: wait until *ok != 0 (bounded), then order later async-proxy (TMA) reads after it
-__device__ __forceinline__ void flag_wait(const int* ok) {
+// `sleep_ns`: pause between polls.  Every poll is an L2 round trip to ONE line; hundreds of threads polling it
+// back to back (ncu r1f: 9.5 G polls/s in k_apply_tc) saturate that L2 slice and delay every tile load that has
+// a sector behind it -- long expected waits must poll slowly.
+__device__ __forceinline__ void flag_wait(const int* ok, uint32_t sleep_ns = 64) {
 #pragma unroll 1
   for (uint32_t i = 0; i < (1u << 26); ++i) {
     if (ld_acquire(ok) != 0) {
@@ -192,7 +216,7 @@ __device__ __forceinline__ void flag_wait(const int* ok) {
       asm volatile("fence.proxy.async.global;" ::: "memory");
       return;
     }
-    __nanosleep(64);
+    __nanosleep(sleep_ns);
   }
   __trap();
 }

@@ -37,8 +37,10 @@ struct TmapKey {
   uint64_t rows, cols;
   uint32_t box_rows;
   int bf;
+  int kind;   // 0: [box_rows x 64] SWIZZLE_128B operand tiles, 1: [32 x 32] SWIZZLE_64B store panels
   bool operator==(const TmapKey& o) const {
-    return base == o.base && rows == o.rows && cols == o.cols && box_rows == o.box_rows && bf == o.bf;
+    return base == o.base && rows == o.rows && cols == o.cols && box_rows == o.box_rows && bf == o.bf &&
+           kind == o.kind;
   }
 };
 struct TmapEntry {
@@ -51,9 +53,9 @@ thread_local int t_cache_n = 0;
 thread_local int t_cache_next = 0;
 }  // namespace
 
-int make_tmap_2d_16b(CUtensorMap* out, int is_bf16, const void* base, uint64_t rows, uint64_t cols,
-                     uint32_t box_rows) {
-  const TmapKey key{base, rows, cols, box_rows, is_bf16};
+static int make_tmap_kind(CUtensorMap* out, int is_bf16, const void* base, uint64_t rows, uint64_t cols,
+                          uint32_t box_rows, int kind) {
+  const TmapKey key{base, rows, cols, box_rows, is_bf16, kind};
   for (int i = 0; i < t_cache_n; ++i) {
     if (t_cache[i].key == key) {
       *out = t_cache[i].map;
@@ -62,17 +64,18 @@ int make_tmap_2d_16b(CUtensorMap* out, int is_bf16, const void* base, uint64_t r
   }
   int s = tmap_init();
   if (s != NNCONV_OK) return s;
-  NNC_REQUIRE(cols % 64 == 0 && rows > 0 && box_rows >= 1 && box_rows <= 256, NNCONV_ERR_ARG,
+  NNC_REQUIRE(cols % 64 == 0 && rows > 0 && box_rows >= 1 && box_rows <= 256 && rows < (1ull << 31), NNCONV_ERR_ARG,
               "tmap: bad shape rows=%llu cols=%llu box_rows=%u", (unsigned long long)rows,
               (unsigned long long)cols, box_rows);
   NNC_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, NNCONV_ERR_ARG, "tmap: base not 16B aligned");
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {cols * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t box[2] = {kind == 1 ? 32u : 64u, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                         const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        kind == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NNC_REQUIRE(r == CUDA_SUCCESS, NNCONV_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   TmapEntry& e = t_cache[t_cache_next];
@@ -81,6 +84,15 @@ int make_tmap_2d_16b(CUtensorMap* out, int is_bf16, const void* base, uint64_t r
   t_cache_next = (t_cache_next + 1) % kTmapCache;
   if (t_cache_n < kTmapCache) ++t_cache_n;
   return NNCONV_OK;
+}
+
+int make_tmap_2d_16b(CUtensorMap* out, int is_bf16, const void* base, uint64_t rows, uint64_t cols,
+                     uint32_t box_rows) {
+  return make_tmap_kind(out, is_bf16, base, rows, cols, box_rows, 0);
+}
+
+int make_tmap_store_16b(CUtensorMap* out, int is_bf16, const void* base, uint64_t rows, uint64_t cols) {
+  return make_tmap_kind(out, is_bf16, base, rows, cols, 32, 1);
 }
 
 // ---- tracing buffer (debug) ------------------------------------------------------------------------

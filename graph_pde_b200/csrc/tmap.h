@@ -12,5 +12,8 @@ int tmap_init();
 // 128-byte swizzle (the layout tcgen05 K-major SW128 descriptors expect).
 int make_tmap_2d_16b(CUtensorMap* out, int is_bf16, const void* base, uint64_t rows, uint64_t cols,
                      uint32_t box_rows);
+// same tensor, described for the GEMM epilogue's TMA stores: box = [32 rows, 32 cols], 64-byte swizzle
+// (one warp's 32 x 32 output piece, 2 KB of shared memory).
+int make_tmap_store_16b(CUtensorMap* out, int is_bf16, const void* base, uint64_t rows, uint64_t cols);
 
 }  // namespace nnc
