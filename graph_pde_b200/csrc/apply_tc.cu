@@ -106,7 +106,8 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
   int4* q_ent = reinterpret_cast<int4*>(q_empty + kQueue);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ent + kQueue);
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  // shfl: the warp index is warp-uniform for the compiler (see tc05::elect_one)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x / 32), 0), lane = threadIdx.x % 32;
   const unsigned long long tr0 = a.trace.rec ? gtime() : 0ull;
 
   if (warp == 0 && lane == 0) {
@@ -154,86 +155,114 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
   // The producer thread grabs units and publishes them to the MMA / epilogue warps through a small
   // shared-memory queue: entry = {first tile, #tiles (0 = end of this CTA's share of batch b, -1 = done), c, b}.
   if (warp == 0) {
-    if (lane == 0) {
-      // ============================================================ contraction: TMA producer + scheduler
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t ld = 0;
-      int qi = 0;
-      uint32_t qph = 0;
-      auto publish = [&](int t, int u, int c, int b) {
-        mbar_wait(&q_empty[qi], qph ^ 1u);
+    // ============================================================== contraction: TMA producer + scheduler
+    // (whole warp runs the loops; the elected lane issues -- see tc05::elect_one)
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t ld = 0;
+    int qi = 0;
+    uint32_t qph = 0;
+    auto publish = [&](int t, int u, int c, int b) {
+      mbar_wait(&q_empty[qi], qph ^ 1u);
+      if (elect_one()) {
         q_ent[qi] = make_int4(t, u, c, b);
         mbar_arrive(&q_full[qi]);                         // release: entry visible to the waiters
-        if (++qi == kQueue) { qi = 0; qph ^= 1u; }
-      };
-      // ONE unit counter for the whole application: units are globally ordered by source, so the batch of
-      // a unit follows from its source (b = c / nb); the grab of the next unit is always in flight while the
-      // current one streams (no exposed atomic round trip at batch boundaries).
-      const int n_units = __ldg(a.unit_ptr + a.n_src);
-      int nxt = atomicAdd(a.cntU, 1);
-      int cur_b = -1;
-      while (nxt < n_units) {
-        const int ui = nxt;
-        nxt = atomicAdd(a.cntU, 1);                       // grab the NEXT unit now
-        const int ut = __ldg(a.unit_t + ui), uu = __ldg(a.unit_u + ui);
-        const int uc = a.tile_c[ut];
-        const int b = uc / a.nb;
-        if (b != cur_b) {
-          const unsigned long long tw0 = a.trace.rec ? gtime() : 0ull;
-          flag_wait(a.okY + b);                           // Y of this batch is complete (and visible to TMA)
-          if (a.trace.rec && (blockIdx.x % 37) == 0)
-            trace_write(a.trace, 301u | (static_cast<unsigned>(b) << 12), tw0, gtime(), 0ull);
-          cur_b = b;
-        }
-        const int ring_row0 = (b % a.ring) * a.nb - b * a.nb;
-        publish(ut, uu, uc, b);
-        for (int p = 0; p < a.passes; ++p) {
-          for (int ti = 0; ti < uu; ++ti) {
-            const int e0 = a.tile_e0[ut + ti];
-            const int box = (a.tile_cnt[ut + ti] + 15) >> 4;
+      }
+      __syncwarp();
+      if (++qi == kQueue) { qi = 0; qph ^= 1u; }
+    };
+    // ONE unit counter for the whole application: units are globally ordered by source, so the batch of
+    // a unit follows from its source (b = c / nb); the grab of the next unit is always in flight while the
+    // current one streams (no exposed atomic round trip at batch boundaries).
+    auto grab = [&]() {
+      int v = 0;
+      if (lane == 0) v = atomicAdd(a.cntU, 1);
+      return __shfl_sync(0xffffffffu, v, 0);
+    };
+    const int n_units = __ldg(a.unit_ptr + a.n_src);
+    int nxt = grab();
+    int cur_b = -1;
+    while (nxt < n_units) {
+      const int ui = nxt;
+      nxt = grab();                                       // grab the NEXT unit now
+      const int ut = __shfl_sync(0xffffffffu, __ldg(a.unit_t + ui), 0);
+      const int uu = __shfl_sync(0xffffffffu, __ldg(a.unit_u + ui), 0);
+      const int uc = __shfl_sync(0xffffffffu, __ldg(a.tile_c + ut), 0);
+      const int b = uc / a.nb;
+      if (b != cur_b) {
+        const unsigned long long tw0 = a.trace.rec ? gtime() : 0ull;
+        if (lane == 0) flag_wait(a.okY + b);              // Y of this batch is complete (and visible to TMA)
+        __syncwarp();
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        if (a.trace.rec && lane == 0 && (blockIdx.x % 37) == 0)
+          trace_write(a.trace, 301u | (static_cast<unsigned>(b) << 12), tw0, gtime(), 0ull);
+        cur_b = b;
+      }
+      const int ring_row0 = (b % a.ring) * a.nb - b * a.nb;
+      publish(ut, uu, uc, b);
+      int te0[kTU], tbox[kTU];
+#pragma unroll
+      for (int ti = 0; ti < kTU; ++ti) {
+        te0[ti] = ti < uu ? __shfl_sync(0xffffffffu, __ldg(a.tile_e0 + ut + ti), 0) : 0;
+        tbox[ti] = ti < uu ? (__shfl_sync(0xffffffffu, __ldg(a.tile_cnt + ut + ti), 0) + 15) >> 4 : 1;
+      }
+      for (int p = 0; p < a.passes; ++p) {
+#pragma unroll
+        for (int ti = 0; ti < kTU; ++ti) {
+          if (ti < uu) {
+            const int e0 = te0[ti];
+            const int box = tbox[ti];
             const CUtensorMap* mh = &tmH.m[box - 1];
             const uint32_t a_bytes = static_cast<uint32_t>(box) * 16u * 128u;
             for (int s = 0; s < a.nb_slots; ++s) {
               const int j = p * a.nb_slots + s;
               if (ti == 0) {
                 mbar_wait(&b_empty[s], (ld & 1u) ^ 1u);
-                mbar_arrive_expect_tx(&b_full[s], b_chunk_bytes);
-                tma_load_2d(smem_b + s * b_stride, &tmY, &b_full[s], j * 64, (ring_row0 + uc) * a.cout, kEvictLast);
+                if (elect_one()) {
+                  mbar_arrive_expect_tx(&b_full[s], b_chunk_bytes);
+                  tma_load_2d(smem_b + s * b_stride, &tmY, &b_full[s], j * 64, (ring_row0 + uc) * a.cout, kEvictLast);
+                }
+                __syncwarp();
               }
               mbar_wait(&a_empty[stage], phase ^ 1u);
-              mbar_arrive_expect_tx(&a_full[stage], a_bytes);
-              tma_load_2d(smem_a + stage * kATileBytes, mh, &a_full[stage], 0, j * a.e_pad + e0, kEvictFirst);
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&a_full[stage], a_bytes);
+                tma_load_2d(smem_a + stage * kATileBytes, mh, &a_full[stage], 0, j * a.e_pad + e0, kEvictFirst);
+              }
+              __syncwarp();
               if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
             }
           }
-          ++ld;
         }
+        ++ld;
       }
-      publish(0, -1, 0, 0);
     }
+    publish(0, -1, 0, 0);
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ============================================================ contraction: MMA issuer
-      const uint32_t idesc = idesc_f16(FMT, 128, static_cast<uint32_t>(a.cout));
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t ld = 0;
-      int it = 0;
-      int qi = 0;
-      uint32_t qph = 0;
-      for (;;) {
-        mbar_wait(&q_full[qi], qph);
-        const int4 en = q_ent[qi];
-        mbar_arrive(&q_empty[qi]);
-        if (++qi == kQueue) { qi = 0; qph ^= 1u; }
-        if (en.y < 0) break;
-        if (en.y == 0) continue;
-        const int as = it & 1;
-        mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1u);
-        fence_after_sync();
-        for (int p = 0; p < a.passes; ++p) {
-          for (int ti = 0; ti < en.y; ++ti) {
+    // ============================================================== contraction: MMA issuer (whole warp, elected lane)
+    const uint32_t idesc = idesc_f16(FMT, 128, static_cast<uint32_t>(a.cout));
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t ld = 0;
+    int it = 0;
+    int qi = 0;
+    uint32_t qph = 0;
+    for (;;) {
+      mbar_wait(&q_full[qi], qph);
+      const int4 en0 = q_ent[qi];
+      const int en_y = __shfl_sync(0xffffffffu, en0.y, 0);
+      __syncwarp();
+      if (elect_one()) mbar_arrive(&q_empty[qi]);
+      if (++qi == kQueue) { qi = 0; qph ^= 1u; }
+      if (en_y < 0) break;
+      if (en_y == 0) continue;
+      const int as = it & 1;
+      mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1u);
+      fence_after_sync();
+      for (int p = 0; p < a.passes; ++p) {
+#pragma unroll
+        for (int ti = 0; ti < kTU; ++ti) {
+          if (ti < en_y) {
             const uint32_t d_tmem = tmem_base + (as * kTU + ti) * a.cout;
             for (int s = 0; s < a.nb_slots; ++s) {
               if (ti == 0) mbar_wait(&b_full[s], ld & 1u);
@@ -241,18 +270,22 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
               fence_after_sync();
               const uint64_t adesc = smem_desc_sw128(smem_u32(smem_a + stage * kATileBytes));
               const uint64_t bdesc = smem_desc_sw128(smem_u32(smem_b + s * b_stride));
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (p | s | k) != 0);
-              umma_commit(&a_empty[stage]);
-              if (ti == en.y - 1) umma_commit(&b_empty[s]);    // B is re-loaded for every (unit, pass)
+                for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (p | s | k) != 0);
+                umma_commit(&a_empty[stage]);
+                if (ti == en_y - 1) umma_commit(&b_empty[s]);    // B is re-loaded for every (unit, pass)
+              }
+              __syncwarp();
               if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
             }
           }
-          ++ld;
         }
-        umma_commit(&tfull[as]);
-        ++it;
+        ++ld;
       }
+      if (elect_one()) umma_commit(&tfull[as]);
+      __syncwarp();
+      ++it;
     }
   } else if (warp < 6) {
     // ================================================================ contraction: epilogue warps 2..5
@@ -327,56 +360,58 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
       ++it;
     }
   } else if (warp == 6) {
-    if (lane == 0) {
-      // ============================================================ Y GEMM: TMA producer
-      const int n_blocks = a.NY / kYBlockN;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int b = 0; b < a.n_batches; ++b) {
-        const int c0 = b * a.nb;
-        const int rows = min(a.nb, a.n_src - c0);
-        const int tiles = ((rows + 127) / 128) * n_blocks;
-        for (int i = static_cast<int>((blockIdx.x + 7u * b) % gridDim.x); i < tiles; i += gridDim.x) {
-          const int mb = i / n_blocks, nbk = i % n_blocks;
-          for (int kx = 0; kx < a.num_kx; ++kx) {
-            mbar_wait(&y_empty[stage], phase ^ 1u);
+    // ============================================================== Y GEMM: TMA producer (whole warp, elected lane)
+    const int n_blocks = a.NY / kYBlockN;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int b = 0; b < a.n_batches; ++b) {
+      const int c0 = b * a.nb;
+      const int rows = min(a.nb, a.n_src - c0);
+      const int tiles = ((rows + 127) / 128) * n_blocks;
+      for (int i = static_cast<int>((blockIdx.x + 7u * b) % gridDim.x); i < tiles; i += gridDim.x) {
+        const int mb = i / n_blocks, nbk = i % n_blocks;
+        for (int kx = 0; kx < a.num_kx; ++kx) {
+          mbar_wait(&y_empty[stage], phase ^ 1u);
+          if (elect_one()) {
             mbar_arrive_expect_tx(&y_full[stage], kYStageBytes);
             uint8_t* st = smem_y + stage * kYStageBytes;
             tma_load_2d(st, &tmX, &y_full[stage], kx * 64, c0 + mb * 128, kEvictLast);
             tma_load_2d(st + kATileBytes, &tmW, &y_full[stage], kx * 64, nbk * kYBlockN, kEvictLast);
-            if (++stage == kYStages) { stage = 0; phase ^= 1u; }
           }
+          __syncwarp();
+          if (++stage == kYStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 7) {
-    if (lane == 0) {
-      // ============================================================ Y GEMM: MMA issuer
-      constexpr uint32_t idesc = idesc_f16(FMT, 128, kYBlockN);
-      const int n_blocks = a.NY / kYBlockN;
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int b = 0; b < a.n_batches; ++b) {
-        const int c0 = b * a.nb;
-        const int rows = min(a.nb, a.n_src - c0);
-        const int tiles = ((rows + 127) / 128) * n_blocks;
-        for (int i = static_cast<int>((blockIdx.x + 7u * b) % gridDim.x); i < tiles; i += gridDim.x, ++it) {
-          const int ys = it & 1;
-          mbar_wait(&yt_empty[ys], ((it >> 1) & 1) ^ 1u);
+    // ============================================================== Y GEMM: MMA issuer (whole warp, elected lane)
+    constexpr uint32_t idesc = idesc_f16(FMT, 128, kYBlockN);
+    const int n_blocks = a.NY / kYBlockN;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int b = 0; b < a.n_batches; ++b) {
+      const int c0 = b * a.nb;
+      const int rows = min(a.nb, a.n_src - c0);
+      const int tiles = ((rows + 127) / 128) * n_blocks;
+      for (int i = static_cast<int>((blockIdx.x + 7u * b) % gridDim.x); i < tiles; i += gridDim.x, ++it) {
+        const int ys = it & 1;
+        mbar_wait(&yt_empty[ys], ((it >> 1) & 1) ^ 1u);
+        fence_after_sync();
+        for (int kx = 0; kx < a.num_kx; ++kx) {
+          mbar_wait(&y_full[stage], phase);
           fence_after_sync();
-          for (int kx = 0; kx < a.num_kx; ++kx) {
-            mbar_wait(&y_full[stage], phase);
-            fence_after_sync();
-            uint8_t* st = smem_y + stage * kYStageBytes;
-            const uint64_t adesc = smem_desc_sw128(smem_u32(st));
-            const uint64_t bdesc = smem_desc_sw128(smem_u32(st + kATileBytes));
+          uint8_t* st = smem_y + stage * kYStageBytes;
+          const uint64_t adesc = smem_desc_sw128(smem_u32(st));
+          const uint64_t bdesc = smem_desc_sw128(smem_u32(st + kATileBytes));
+          if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16(tmem_y + ys * kYBlockN, adesc + 2 * k, bdesc + 2 * k, idesc, (kx | k) != 0);
             umma_commit(&y_empty[stage]);
             if (kx == a.num_kx - 1) umma_commit(&yt_full[ys]);
-            if (++stage == kYStages) { stage = 0; phase ^= 1u; }
           }
+          __syncwarp();
+          if (++stage == kYStages) { stage = 0; phase ^= 1u; }
         }
       }
     }

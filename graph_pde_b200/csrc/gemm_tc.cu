@@ -80,7 +80,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  // shfl: the warp index is warp-uniform for the compiler (role branches converge, operands stay in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x / 32), 0), lane = threadIdx.x % 32;
   const int m_blocks = ceil_div(a.M, Cfg::kBlockM);
   const int n_blocks = ceil_div(a.N, BLOCK_N);
   const int num_tiles = m_blocks * n_blocks;
@@ -114,40 +115,41 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ TMA producer
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int mb = t / n_blocks, nb = t % n_blocks;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1u);
+    // -------------------------------------------------------------- TMA producer (whole warp, elected lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int mb = t / n_blocks, nb = t % n_blocks;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
           tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full[stage], kb * Cfg::kBlockK,
                       a.a_row0 + mb * Cfg::kBlockM, kEvictNormal);
           tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full[stage], kb * Cfg::kBlockK, nb * BLOCK_N,
                       kEvictLast);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc = idesc_f16(FMT, Cfg::kBlockM, BLOCK_N);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int as = it & 1;
-        mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1u);
+    // -------------------------------------------------------------- MMA issuer (whole warp, elected lane issues)
+    constexpr uint32_t idesc = idesc_f16(FMT, Cfg::kBlockM, BLOCK_N);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1u);
+      fence_after_sync();
+      const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
         fence_after_sync();
-        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          fence_after_sync();
-          const uint64_t adesc = smem_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
-          const uint64_t bdesc = smem_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+        const uint64_t adesc = smem_desc_sw128(smem_u32(smem_a + stage * Cfg::kABytes));
+        const uint64_t bdesc = smem_desc_sw128(smem_u32(smem_b + stage * Cfg::kBBytes));
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < Cfg::kBlockK / 16; ++k) {
             // advance 16 elements (32 bytes) along K inside the 128B swizzle span: +2 in 16-byte units
@@ -155,8 +157,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           umma_commit(&empty[stage]);           // frees the smem slot once these MMAs have read it
           if (kb == num_kb - 1) umma_commit(&tfull[as]);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -225,7 +228,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           }
           if (use_tma) {
             const uint32_t buf = stage0 + (piece & 1) * 2048;
-            if (lane == 0) bulk_wait_read1();                 // the store issued two pieces ago has left this buffer
+            const bool issuer = elect_one();                  // same lane every time: bulk groups are per thread
+            if (issuer) bulk_wait_read1();                    // the store issued two pieces ago has left this buffer
             __syncwarp();
 #pragma unroll
             for (int u = 0; u < 4; ++u)
@@ -233,7 +237,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                            packed[4 * u + 2], packed[4 * u + 3]);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (issuer) {
               const int r0 = mb * Cfg::kBlockM + quarter * 32;
               if (a.chunk_rows_pad > 0)
                 tma_store_2d(&tmC, buf, col0 & 63,
@@ -259,7 +263,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       if (lane == 0) mbar_arrive(&tempty[as]);
     }
   }
-  if (Cfg::kStoreBytes > 0 && a.tma_store && warp >= 2 && lane == 0) bulk_wait0();
+  if (Cfg::kStoreBytes > 0 && a.tma_store && warp >= 2 && elect_one()) bulk_wait0();
   fence_before_sync();
   if (a.done_cnt != nullptr) signal_done(a.done_cnt, a.done_ok);   // includes __syncthreads
   else __syncthreads();

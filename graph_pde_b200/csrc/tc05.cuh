@@ -90,6 +90,16 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// One lane of a CONVERGED warp (elect.sync).  Role loops run on all 32 lanes and only issue through the elected
+// lane: operands computed in converged code are warp-uniform for the compiler (uniform registers), whereas
+// inside an `if (lane == 0)` region every tcgen05 / TMA / mbarrier instruction is wrapped in an
+// ELECT / R2UR / BRA.U.ANY waterfall loop (~45 cycles each, ncu r1f source view).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
