@@ -159,7 +159,9 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
     // (whole warp runs the loops; the elected lane issues -- see tc05::elect_one)
     int stage = 0;
     uint32_t phase = 0;
-    uint32_t ld = 0;
+    int bs = 0;               // B slot ring (one slot per K chunk of the current unit's Y slice)
+    uint32_t bph = 0;
+    const int num_kc = a.passes * a.nb_slots;
     int qi = 0;
     uint32_t qph = 0;
     auto publish = [&](int t, int u, int c, int b) {
@@ -206,35 +208,31 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
         te0[ti] = ti < uu ? __shfl_sync(0xffffffffu, __ldg(a.tile_e0 + ut + ti), 0) : 0;
         tbox[ti] = ti < uu ? (__shfl_sync(0xffffffffu, __ldg(a.tile_cnt + ut + ti), 0) + 15) >> 4 : 1;
       }
-      for (int p = 0; p < a.passes; ++p) {
+      // K chunk outer, tile inner: the B slot of chunk j is released after the unit's LAST tile and needed again
+      // only nb_slots chunks later, i.e. 2*nb_slots - 1 MMA blocks for a 2-tile unit (with a pass-major order it
+      // was nb_slots - 1 and the MMA warp spent 20% of its time waiting for B, ncu r1g)
+      for (int j = 0; j < num_kc; ++j) {
+        mbar_wait(&b_empty[bs], bph ^ 1u);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&b_full[bs], b_chunk_bytes);
+          tma_load_2d(smem_b + bs * b_stride, &tmY, &b_full[bs], j * 64, (ring_row0 + uc) * a.cout, kEvictLast);
+        }
+        __syncwarp();
+        if (++bs == a.nb_slots) { bs = 0; bph ^= 1u; }
 #pragma unroll
         for (int ti = 0; ti < kTU; ++ti) {
           if (ti < uu) {
-            const int e0 = te0[ti];
-            const int box = tbox[ti];
-            const CUtensorMap* mh = &tmH.m[box - 1];
-            const uint32_t a_bytes = static_cast<uint32_t>(box) * 16u * 128u;
-            for (int s = 0; s < a.nb_slots; ++s) {
-              const int j = p * a.nb_slots + s;
-              if (ti == 0) {
-                mbar_wait(&b_empty[s], (ld & 1u) ^ 1u);
-                if (elect_one()) {
-                  mbar_arrive_expect_tx(&b_full[s], b_chunk_bytes);
-                  tma_load_2d(smem_b + s * b_stride, &tmY, &b_full[s], j * 64, (ring_row0 + uc) * a.cout, kEvictLast);
-                }
-                __syncwarp();
-              }
-              mbar_wait(&a_empty[stage], phase ^ 1u);
-              if (elect_one()) {
-                mbar_arrive_expect_tx(&a_full[stage], a_bytes);
-                tma_load_2d(smem_a + stage * kATileBytes, mh, &a_full[stage], 0, j * a.e_pad + e0, kEvictFirst);
-              }
-              __syncwarp();
-              if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
+            const CUtensorMap* mh = &tmH.m[tbox[ti] - 1];
+            const uint32_t a_bytes = static_cast<uint32_t>(tbox[ti]) * 16u * 128u;
+            mbar_wait(&a_empty[stage], phase ^ 1u);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&a_full[stage], a_bytes);
+              tma_load_2d(smem_a + stage * kATileBytes, mh, &a_full[stage], 0, j * a.e_pad + te0[ti], kEvictFirst);
             }
+            __syncwarp();
+            if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
           }
         }
-        ++ld;
       }
     }
     publish(0, -1, 0, 0);
@@ -243,7 +241,9 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
     const uint32_t idesc = idesc_f16(FMT, 128, static_cast<uint32_t>(a.cout));
     int stage = 0;
     uint32_t phase = 0;
-    uint32_t ld = 0;
+    int bs = 0;
+    uint32_t bph = 0;
+    const int num_kc = a.passes * a.nb_slots;
     int it = 0;
     int qi = 0;
     uint32_t qph = 0;
@@ -259,29 +259,27 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
       const int as = it & 1;
       mbar_wait(&tempty[as], ((it >> 1) & 1) ^ 1u);
       fence_after_sync();
-      for (int p = 0; p < a.passes; ++p) {
+      for (int j = 0; j < num_kc; ++j) {
+        mbar_wait(&b_full[bs], bph);
+        const uint64_t bdesc = smem_desc_sw128(smem_u32(smem_b + bs * b_stride));
 #pragma unroll
         for (int ti = 0; ti < kTU; ++ti) {
           if (ti < en_y) {
             const uint32_t d_tmem = tmem_base + (as * kTU + ti) * a.cout;
-            for (int s = 0; s < a.nb_slots; ++s) {
-              if (ti == 0) mbar_wait(&b_full[s], ld & 1u);
-              mbar_wait(&a_full[stage], phase);
-              fence_after_sync();
-              const uint64_t adesc = smem_desc_sw128(smem_u32(smem_a + stage * kATileBytes));
-              const uint64_t bdesc = smem_desc_sw128(smem_u32(smem_b + s * b_stride));
-              if (elect_one()) {
+            mbar_wait(&a_full[stage], phase);
+            fence_after_sync();
+            const uint64_t adesc = smem_desc_sw128(smem_u32(smem_a + stage * kATileBytes));
+            if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (p | s | k) != 0);
-                umma_commit(&a_empty[stage]);
-                if (ti == en_y - 1) umma_commit(&b_empty[s]);    // B is re-loaded for every (unit, pass)
-              }
-              __syncwarp();
-              if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
+              for (int k = 0; k < 4; ++k) umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (j | k) != 0);
+              umma_commit(&a_empty[stage]);
+              if (ti == en_y - 1) umma_commit(&b_empty[bs]);    // B is re-loaded for every unit
             }
+            __syncwarp();
+            if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
           }
         }
-        ++ld;
+        if (++bs == a.nb_slots) { bs = 0; bph ^= 1u; }
       }
       if (elect_one()) umma_commit(&tfull[as]);
       __syncwarp();
