@@ -301,7 +301,7 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
 // one conv application
 // ------------------------------------------------------------------------------------------------
 struct ApplyLayout {
-  size_t off_Xc, off_cvec, off_flags, off_Y, fixed_bytes, per_node;
+  size_t off_Xc, off_cvec, off_xs, off_flags, off_Y, fixed_bytes, per_node;
 };
 constexpr int kMaxPipeBatches = 1 << 14;   // flags: cntY, cntC, okY, okC per batch
 
@@ -311,6 +311,7 @@ static ApplyLayout layout_apply(const Plan* P, const Weights* W) {
   const size_t S = P->n_src > 0 ? P->n_src : 1;
   L.off_Xc = c.off; c.take<char>((S + 128) * W->cin_p * W->esize);
   L.off_cvec = c.off; c.take<float>(S * W->cout);
+  L.off_xs = c.off; c.take<float>(S);
   L.off_flags = c.off; c.take<int>(5 * kMaxPipeBatches);
   L.off_Y = c.off;
   L.fixed_bytes = c.off;
@@ -345,11 +346,12 @@ int apply(const Plan* P, const Weights* W, const void* h, const float* x, const 
   char* base = static_cast<char*>(ws);
   void* Xc = base + L.off_Xc;
   float* cvec = reinterpret_cast<float*>(base + L.off_cvec);
+  float* xs = reinterpret_cast<float*>(base + L.off_xs);
   void* Y = base + L.off_Y;
   int64_t nodes_cap = static_cast<int64_t>((ws_bytes - L.fixed_bytes) / L.per_node);
   {
     ProfScope ps(PK_NODE_PREP, st);
-    s = launch_src_prep(W->prec, x, P->src_nodes, P->n_src, W->cin, W->cin_p, W->cout, W->B3, Xc, cvec, st);
+    s = launch_src_prep(W->prec, x, P->src_nodes, P->n_src, W->cin, W->cin_p, W->cout, W->B3, Xc, cvec, xs, st);
   }
   if (s) return s;
   if (launches) ++*launches;
@@ -395,7 +397,7 @@ int apply(const Plan* P, const Weights* W, const void* h, const float* x, const 
       NNC_CHECK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 5 * kMaxPipeBatches, st));
       {
         ProfScope ps(PK_APPLY_FUSED, st);
-        s = launch_apply_tc(W->prec, P, W, h, Xc, Y, static_cast<int>(nb), ring, cvec, aggr_mean, out, flags,
+        s = launch_apply_tc(W->prec, P, W, h, Xc, Y, static_cast<int>(nb), ring, cvec, xs, aggr_mean, out, flags,
                             kMaxPipeBatches, st);
       }
       if (s) return s;
@@ -456,7 +458,7 @@ int apply(const Plan* P, const Weights* W, const void* h, const float* x, const 
       pf.join_n = static_cast<int>(n_batches - 1);
     }
     ProfScope ps(PK_CONV, st);
-    return launch_conv_tc(W->prec, P, h, W->Kp, Ybuf[b % 3], nb, W->cout, tb, te, static_cast<int>(c0), cvec,
+    return launch_conv_tc(W->prec, P, h, W->Kp, Ybuf[b % 3], nb, W->cout, tb, te, static_cast<int>(c0), cvec, xs,
                           aggr_mean, out, st, pipe ? &pf : nullptr);
   };
   s = launch_y(0);

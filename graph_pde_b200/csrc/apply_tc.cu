@@ -49,6 +49,7 @@ struct ApplyArgs {
   const int* dst_sorted;
   const float* inv_deg;   // nullptr -> aggr = add
   const float* cvec;      // [S, cout]
+  const float* xs;        // [S] power-of-two row scale of the Y operand (see k_src_prep)
   float* out;             // [N, cout]
   int n_src, nb, n_batches, ring;
   int cout, nb_slots, passes, a_stages, e_pad;
@@ -315,6 +316,7 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
         }
       }
       const float* cv = a.cvec + static_cast<int64_t>(en.z) * a.cout;
+      const float xsc = __ldg(a.xs + en.z);
       mbar_wait(&tfull[as], (it >> 1) & 1);
       fence_after_sync();
       if (warp == 2 && lane == 0) {
@@ -343,10 +345,10 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const float4 cq = __ldg(reinterpret_cast<const float4*>(cv + cc) + q);
-                red_add_v4(orow + cc + 4 * q, (__uint_as_float(v[4 * q + 0]) + cq.x) * sc[ti],
-                           (__uint_as_float(v[4 * q + 1]) + cq.y) * sc[ti],
-                           (__uint_as_float(v[4 * q + 2]) + cq.z) * sc[ti],
-                           (__uint_as_float(v[4 * q + 3]) + cq.w) * sc[ti]);
+                red_add_v4(orow + cc + 4 * q, fmaf(__uint_as_float(v[4 * q + 0]), xsc, cq.x) * sc[ti],
+                           fmaf(__uint_as_float(v[4 * q + 1]), xsc, cq.y) * sc[ti],
+                           fmaf(__uint_as_float(v[4 * q + 2]), xsc, cq.z) * sc[ti],
+                           fmaf(__uint_as_float(v[4 * q + 3]), xsc, cq.w) * sc[ti]);
               }
             }
           }
@@ -535,8 +537,8 @@ bool apply_fused_supported(const Weights* W) {
 }
 
 int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, const void* Xc, void* Yring, int nb,
-                    int ring, const float* cvec, int aggr_mean, float* out, int* flags, int flags_stride,
-                    cudaStream_t st) {
+                    int ring, const float* cvec, const float* xs, int aggr_mean, float* out, int* flags,
+                    int flags_stride, cudaStream_t st) {
   int s = tc_init();
   if (s != NNCONV_OK) return s;
   const int bf = prec == PREC_BF16;
@@ -563,7 +565,7 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
   ApplyArgs a;
   a.tile_c = P->tile_c; a.tile_e0 = P->tile_e0; a.tile_cnt = P->tile_cnt; a.tile_ptr = P->tile_ptr;
   a.unit_ptr = P->unit_ptr; a.unit_t = P->unit_t; a.unit_u = P->unit_u;
-  a.dst_sorted = P->dst_sorted; a.inv_deg = aggr_mean ? P->inv_deg : nullptr; a.cvec = cvec; a.out = out;
+  a.dst_sorted = P->dst_sorted; a.inv_deg = aggr_mean ? P->inv_deg : nullptr; a.cvec = cvec; a.xs = xs; a.out = out;
   a.n_src = P->n_src; a.nb = nb; a.n_batches = n_batches; a.ring = ring;
   a.cout = W->cout; a.nb_slots = as.nb_slots; a.passes = as.passes; a.a_stages = as.a_stages;
   a.e_pad = static_cast<int>(e_pad);

@@ -289,7 +289,7 @@ int backward_fp32(const Plan* P, const Weights* W, const float* edge_attr, const
   float* Xc = reinterpret_cast<float*>(base + L.off_Xc);
   float* cvec = reinterpret_cast<float*>(base + L.off_cvec);
   if (P->E > 0 && P->n_src > 0) {
-    s = launch_src_prep(PREC_FP32, x, P->src_nodes, P->n_src, cin, cin_p, cout, W->B3, Xc, cvec, st);
+    s = launch_src_prep(PREC_FP32, x, P->src_nodes, P->n_src, cin, cin_p, cout, W->B3, Xc, cvec, nullptr, st);
     if (s) return s;
     // batch of sources bounded by the workspace
     const int* hgp = P->h_group_ptr;

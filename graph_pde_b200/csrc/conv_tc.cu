@@ -53,6 +53,7 @@ struct ConvTcArgs {
   const int* dst_sorted;
   const float* inv_deg;   // nullptr -> aggr = add
   const float* cvec;      // [S, cout]
+  const float* xs;        // [S] power-of-two row scale of the Y operand (see k_src_prep)
   float* out;             // [N, cout]
   int tile_begin, tile_end;
   int c0;                 // compact source index of Y row block 0
@@ -248,6 +249,7 @@ k_conv_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMap
         }
       }
       const float* cv = a.cvec + static_cast<int64_t>(un.c) * a.cout;
+      const float xsc = __ldg(a.xs + un.c);
       mbar_wait(&tfull[as], (it >> 1) & 1);
       fence_after_sync();
 #pragma unroll
@@ -263,10 +265,10 @@ k_conv_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMap
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const float4 cq = __ldg(reinterpret_cast<const float4*>(cv + cc) + q);
-                red_add_v4(orow + cc + 4 * q, (__uint_as_float(v[4 * q + 0]) + cq.x) * sc[ti],
-                           (__uint_as_float(v[4 * q + 1]) + cq.y) * sc[ti],
-                           (__uint_as_float(v[4 * q + 2]) + cq.z) * sc[ti],
-                           (__uint_as_float(v[4 * q + 3]) + cq.w) * sc[ti]);
+                red_add_v4(orow + cc + 4 * q, fmaf(__uint_as_float(v[4 * q + 0]), xsc, cq.x) * sc[ti],
+                           fmaf(__uint_as_float(v[4 * q + 1]), xsc, cq.y) * sc[ti],
+                           fmaf(__uint_as_float(v[4 * q + 2]), xsc, cq.z) * sc[ti],
+                           fmaf(__uint_as_float(v[4 * q + 3]), xsc, cq.w) * sc[ti]);
               }
             }
           }
@@ -336,7 +338,7 @@ bool tc_shapes_supported(const Weights* W) {
 }
 
 int launch_conv_tc(int prec, const Plan* P, const void* h, int Kp, const void* Y, int64_t y_nodes, int cout,
-                   int tile_begin, int tile_end, int c0, const float* cvec, int aggr_mean, float* out,
+                   int tile_begin, int tile_end, int c0, const float* cvec, const float* xs, int aggr_mean, float* out,
                    cudaStream_t st, const PipeFlags* pf) {
   if (tile_end <= tile_begin) return NNCONV_OK;
   int s = tc_init();
@@ -358,7 +360,7 @@ int launch_conv_tc(int prec, const Plan* P, const void* h, int Kp, const void* Y
   ConvTcArgs a;
   a.e_pad = static_cast<int>(e_pad);
   a.tile_c = P->tile_c; a.tile_e0 = P->tile_e0; a.tile_cnt = P->tile_cnt; a.dst_sorted = P->dst_sorted;
-  a.inv_deg = aggr_mean ? P->inv_deg : nullptr; a.cvec = cvec; a.out = out;
+  a.inv_deg = aggr_mean ? P->inv_deg : nullptr; a.cvec = cvec; a.xs = xs; a.out = out;
   a.tile_begin = tile_begin; a.tile_end = tile_end; a.c0 = c0; a.cout = cout;
   a.nb_slots = cs.nb_slots; a.passes = cs.passes; a.a_stages = cs.a_stages;
   if (const char* e = getenv("NNCONV_CONV_STAGES")) { int v = atoi(e); if (v >= 2 && v < a.a_stages) a.a_stages = v; }

@@ -17,7 +17,7 @@ int launch_w1aug(int prec, const float* W1, const float* b1, int k1, int kp1, in
 int launch_out_init(const float* x, const float* root, const float* bias, int64_t N, int cin, int cout, float* out,
                     cudaStream_t st);
 int launch_src_prep(int prec, const float* x, const int* src_nodes, int S, int cin, int cin_p, int cout,
-                    const float* B3, void* Xc, float* cvec, cudaStream_t st);
+                    const float* B3, void* Xc, float* cvec, float* xs, cudaStream_t st);
 int launch_sgemm_store(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
                        int K, const float* bias_relu, cudaStream_t st);
 int launch_sgemm_scatter(const Plan* P, const float* h, int Kp, const float* Y, int cout, int tile_begin,
@@ -52,7 +52,7 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
 
 // ---- conv_tc.cu (tcgen05): per-source contraction + scatter for tiles [tile_begin, tile_end)
 int launch_conv_tc(int prec, const Plan* P, const void* h, int Kp, const void* Y, int64_t y_nodes, int cout,
-                   int tile_begin, int tile_end, int c0, const float* cvec, int aggr_mean, float* out,
+                   int tile_begin, int tile_end, int c0, const float* cvec, const float* xs, int aggr_mean, float* out,
                    cudaStream_t st, const PipeFlags* pf = nullptr);
 
 // ---- mlp_fused_tc.cu: first two MLP layers in one kernel (h1 never leaves the SM)
@@ -69,7 +69,8 @@ int launch_mlp_ring_tc(int prec, const void* A1, int64_t rows, int k_in, const v
 // ---- apply_tc.cu: ONE persistent kernel per application (Y GEMM + contraction pipelines in every CTA)
 bool apply_fused_supported(const Weights* W);
 int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, const void* Xc, void* Yring, int nb,
-                    int ring, const float* cvec, int aggr_mean, float* out, int* flags, int flags_stride,
+                    int ring, const float* cvec, const float* xs, int aggr_mean, float* out, int* flags,
+                    int flags_stride,
                     cudaStream_t st);
 
 bool tc_shapes_supported(const Weights* W);

@@ -177,11 +177,16 @@ __global__ void k_out_init(const float* __restrict__ x, const float* __restrict_
   }
 }
 
-// per compact source c: Xc[c, :] = x[src_nodes[c], :] (converted, zero padded to cin_p),
+// per compact source c: Xc[c, :] = x[src_nodes[c], :] / xs[c] (converted, zero padded to cin_p),
 //                       cvec[c, o] = sum_i x[n, i] * B3[i, o]       (bias of the last Linear, reassociated)
+// xs[c] (16-bit paths only) = the power of two >= max_i |x[n, i]| (1 for an all-zero row): the contraction is
+// linear in x, so the operand row is normalised to (0.5, 1] -- exactly, the scale only touches the exponent --
+// and the epilogue multiplies the accumulator by xs[c].  Without it node features beyond the fp16 range
+// (65504; an untrained MGKN V-cycle reaches 5e5 after 4 depth iterations) turned into inf/NaN.
 template <typename T>
 __global__ void k_src_prep(const float* __restrict__ x, const int* __restrict__ src_nodes, int S, int cin, int cin_p,
-                           int cout, const float* __restrict__ B3, T* __restrict__ Xc, float* __restrict__ cvec) {
+                           int cout, const float* __restrict__ B3, T* __restrict__ Xc, float* __restrict__ cvec,
+                           float* __restrict__ xs) {
   extern __shared__ float sx[];
   const int npb = blockDim.y;
   int c = blockIdx.x * npb + threadIdx.y;
@@ -191,8 +196,23 @@ __global__ void k_src_prep(const float* __restrict__ x, const int* __restrict__ 
     for (int i = threadIdx.x; i < cin; i += blockDim.x) myx[i] = x[static_cast<int64_t>(n) * cin + i];
   __syncthreads();
   if (c >= S) return;
+  float inv = 1.f;
+  if (xs != nullptr) {
+    float m = 0.f;
+    for (int i = 0; i < cin; ++i) m = fmaxf(m, fabsf(myx[i]));
+    float sc = 1.f;
+    if (m > 0.f && m <= 3.0e38f) {                 // finite, non-zero: round up to a power of two
+      int e;
+      const float f = frexpf(m, &e);               // m = f * 2^e, f in [0.5, 1)
+      e = f == 0.5f ? e - 1 : e;
+      e = e < -100 ? -100 : (e > 126 ? 126 : e);
+      sc = ldexpf(1.f, e);
+    }
+    inv = 1.f / sc;                                // exact (power of two)
+    if (threadIdx.x == 0) xs[c] = sc;
+  }
   for (int i = threadIdx.x; i < cin_p; i += blockDim.x)
-    Xc[static_cast<int64_t>(c) * cin_p + i] = cvt<T>(i < cin ? myx[i] : 0.f);
+    Xc[static_cast<int64_t>(c) * cin_p + i] = cvt<T>(i < cin ? myx[i] * inv : 0.f);
   for (int o = threadIdx.x; o < cout; o += blockDim.x) {
     float acc = 0.f;
     for (int i = 0; i < cin; ++i) acc = fmaf(myx[i], B3[i * cout + o], acc);
@@ -373,18 +393,18 @@ int launch_out_init(const float* x, const float* root, const float* bias, int64_
 }
 
 int launch_src_prep(int prec, const float* x, const int* src_nodes, int S, int cin, int cin_p, int cout,
-                    const float* B3, void* Xc, float* cvec, cudaStream_t st) {
+                    const float* B3, void* Xc, float* cvec, float* xs, cudaStream_t st) {
   if (S <= 0) return NNCONV_OK;
   dim3 b(64, 4);
   unsigned g = (unsigned)ceil_div(S, (int)b.y);
   size_t sm = sizeof(float) * b.y * cin;
   if (prec == PREC_FP32)
-    k_src_prep<float><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3, static_cast<float*>(Xc), cvec);
+    k_src_prep<float><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3, static_cast<float*>(Xc), cvec, nullptr);
   else if (prec == PREC_F16)
-    k_src_prep<__half><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3, static_cast<__half*>(Xc), cvec);
+    k_src_prep<__half><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3, static_cast<__half*>(Xc), cvec, xs);
   else
     k_src_prep<__nv_bfloat16><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3,
-                                                static_cast<__nv_bfloat16*>(Xc), cvec);
+                                                static_cast<__nv_bfloat16*>(Xc), cvec, xs);
   NNC_CHECK_LAUNCH();
   return NNCONV_OK;
 }

@@ -82,3 +82,40 @@ def test_mgkn_orthogonal_burgers1d(precision):
     with torch.no_grad():
         out = model((X, None, eis, eas))
     assert rel_err(out, t(g['out'])) < TOL[precision]
+
+
+def test_cuda_graph_replay_of_kernelnn_and_vcycle():
+    """the whole forward replayed from a CUDA graph gives the eager result; refreshed static inputs
+    are picked up."""
+    from graph_pde_b200 import GraphedForward
+    from graph_pde_b200.models import KernelInduced, KernelNN
+    g = np.load(os.path.join(GOLDEN, 'g2_cfg1_ball16.npz'))
+    torch.manual_seed(0)
+    model = KernelNN(32, 64, 3, 6, in_width=6).to(DEV).eval()
+    d = _Data()
+    d.x, d.edge_index, d.edge_attr = t(g['node_x']).to(DEV), ei64(g['edge_index']).to(DEV), t(g['edge_attr']).to(DEV)
+    with torch.no_grad():
+        eager = model(d).clone()
+    gf = GraphedForward(model, d)
+    assert rel_err(gf.replay(), eager) < 1e-5
+    x2 = torch.randn_like(d.x)
+    with torch.no_grad():
+        d.x.copy_(x2)
+        eager2 = model(d).clone()
+    assert rel_err(gf.replay(), eager2) < 1e-5
+    assert rel_err(eager2, eager) > 1e-2
+
+    g4 = np.load(os.path.join(GOLDEN, 'g4_mgkn_vcycle.npz'))
+    pts = [int(p) for p in g4['points']]
+    vm = KernelInduced(width=32, ker_width=64, depth=2, ker_in=6, points=pts, level=len(pts), in_width=6)
+    vm = _load(vm, {k[len('neurips1/w/'):]: g4[k] for k in g4.files if k.startswith('neurips1/w/')})
+    dv = _Data()
+    dv.x = t(g4['node_x']).to(DEV)
+    for nm in ('mid', 'down', 'up'):
+        setattr(dv, 'edge_index_' + nm, ei64(g4['edge_index_' + nm]).to(DEV))
+        setattr(dv, 'edge_attr_' + nm, t(g4['edge_attr_' + nm]).to(DEV))
+    dv.edge_index_range = torch.from_numpy(g4['range_mid']).to(DEV)
+    dv.edge_index_down_range = torch.from_numpy(g4['range_down']).to(DEV)
+    dv.edge_index_up_range = torch.from_numpy(g4['range_up']).to(DEV)
+    gv = GraphedForward(vm, dv)
+    assert rel_err(gv.replay(), t(g4['neurips1/out'])) < TOL['f16']
