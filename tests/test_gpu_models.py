@@ -97,12 +97,12 @@ def test_cuda_graph_replay_of_kernelnn_and_vcycle():
     with torch.no_grad():
         eager = model(d).clone()
     gf = GraphedForward(model, d)
-    assert rel_err(gf.replay(), eager) < 1e-5
+    assert rel_err(gf.replay(), eager) < 1e-4      # fp32 atomics: summation order differs run to run
     x2 = torch.randn_like(d.x)
     with torch.no_grad():
         d.x.copy_(x2)
         eager2 = model(d).clone()
-    assert rel_err(gf.replay(), eager2) < 1e-5
+    assert rel_err(gf.replay(), eager2) < 1e-4
     assert rel_err(eager2, eager) > 1e-2
 
     g4 = np.load(os.path.join(GOLDEN, 'g4_mgkn_vcycle.npz'))
