@@ -38,7 +38,7 @@ stats = {'launches': 0, 'plans_built': 0, 'edge_feature_passes': 0, 'applies': 0
 _PLAN_CACHE = collections.OrderedDict()
 _PLAN_CACHE_MAX = int(os.environ.get('NNCONV_B200_PLAN_CACHE', '64'))
 _Y_BYTES = int(os.environ.get('NNCONV_B200_Y_BYTES', str(48 << 20)))       # Y ring: 3 x 128 sources at out=64, Kp=1024
-_EF_WS_BYTES = int(os.environ.get('NNCONV_B200_EF_WS_BYTES', str(1 << 30)))  # hidden-layer ping-pong chunk
+_EF_WS_BYTES = int(os.environ.get('NNCONV_B200_EF_WS_BYTES', str(4 << 30)))  # hidden-layer ping-pong chunk (4 GiB: 25 instead of 97 chunks at 241^2, -1 ms/step, run39)
 _BWD_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_WS_BYTES', str(2 << 30)))  # backward: activations per batch
 
 
