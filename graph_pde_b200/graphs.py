@@ -146,3 +146,55 @@ def multi_level_ball_graph(s, sample_sizes, radius_inner, radius_inter, theta=No
     g.edge_index_range, g.edge_index_down_range, g.edge_index_up_range = ranges(mid), ranges(down), ranges(up)
     g.edge_attr_mid, g.edge_attr_down, g.edge_attr_up = attrs(g.edge_index_mid), attrs(g.edge_index_down), attrs(g.edge_index_up)
     return g
+
+
+# ------------------------------------------------------------------------------------------------------
+# 1-D multipole hierarchy (orthogonal MGKN, Burgers): multi_pole_grid1d restated
+# (multipole-graph-neural-operator/utilities.py:1702-1768), vectorised, any device.
+# ------------------------------------------------------------------------------------------------------
+def multi_pole_grid1d(theta, s, is_periodic=False, levels=None, device='cpu'):
+    """theta: [s] coefficient of ONE sample on the finest grid.  Returns (X_list, edge_index_list, edge_attr_list):
+    level l (1-based) has s_l = s / 2^(l-1) nodes at linspace(0,1,s_l) with theta subsampled by stride 2^(l-1);
+    edge set 0 = nearest neighbours of the finest level (offsets -1,+1), edge set l = 'interactive' neighbours of
+    level l (offsets -3..3 with |offset| >= 2 whose parents are adjacent: |x_i//2 - x_j//2| mod (s_l/2) <= 1), in
+    the reference's (x_i major, offset ascending) order.  edge_attr = [x_src, x_dst, theta_src, theta_dst]
+    (get_edge_attr, utilities.py:1771-1777); X_l = [x, theta_l].  `levels` truncates the hierarchy (the shipped
+    rule int(log2 s - 1) gives 12 levels at s=8192; BASELINE config 5 names 5)."""
+    n_levels = int(math.log2(s) - 1)
+    if levels is not None:
+        n_levels = min(n_levels, int(levels))
+    theta = torch.as_tensor(theta).reshape(-1).to(device)
+
+    def pairs(s_l, offsets, inter):
+        xi = torch.arange(s_l, device=device)[:, None].expand(s_l, len(offsets))
+        off = torch.tensor(offsets, device=device)[None, :].expand(s_l, len(offsets))
+        xj = xi + off
+        if is_periodic:
+            xj = xj % s_l
+            ok = torch.ones_like(xj, dtype=torch.bool)
+        else:
+            ok = (xj >= 0) & (xj < s_l)
+        if inter:
+            par = (torch.div(xi, 2, rounding_mode='floor') - torch.div(xj, 2, rounding_mode='floor')).abs()
+            ok = ok & (par % (s_l // 2) <= 1)
+        return torch.stack([xi[ok], xj[ok]]).long()
+
+    X_list, ei_list, ea_list = [], [], []
+    for l in range(1, n_levels + 1):
+        r_l = 2 ** (l - 1)
+        s_l = s // r_l
+        grid_l = torch.linspace(0.0, 1.0, s_l, dtype=torch.float64, device=device).float()
+        theta_l = theta[::r_l][:s_l].float()
+        X_list.append(torch.stack([grid_l, theta_l], dim=1))
+
+        def attr(e):
+            return torch.stack([grid_l[e[0]], grid_l[e[1]], theta_l[e[0]], theta_l[e[1]]], dim=1).contiguous()
+
+        if l == 1:
+            e = pairs(s_l, [-1, 1], False)
+            ei_list.append(e)
+            ea_list.append(attr(e))
+        e = pairs(s_l, [-3, -2, 2, 3], True)
+        ei_list.append(e)
+        ea_list.append(attr(e))
+    return X_list, ei_list, ea_list

@@ -128,6 +128,25 @@ def test_multilevel_graph_builder_matches_reference_golden():
         assert np.allclose(getattr(g, name).numpy(), g7[key], atol=1e-6), name
 
 
+def test_multipole_grid1d_matches_reference_golden():
+    """graphs.multi_pole_grid1d vs the reference's multi_pole_grid1d + get_edge_attr
+    (multipole-graph-neural-operator/utilities.py:1702-1777) on the periodic s=64 hierarchy stored in G5."""
+    g = np.load(os.path.join(GOLDEN, 'g5_mgkn_burgers1d.npz'))
+    X, ei, ea = graphs.multi_pole_grid1d(g['X/0'][:, 1], int(g['s']), is_periodic=True)
+    assert len(X) == int(g['n_levels']) and len(ei) == int(g['n_edge_sets'])
+    for l in range(len(X)):
+        assert np.allclose(X[l].numpy(), g['X/%d' % l], atol=1e-6)
+    for i in range(len(ei)):
+        assert np.array_equal(ei[i].numpy(), g['edge_index/%d' % i].astype(np.int64))
+        assert np.allclose(ea[i].numpy(), g['edge_attr/%d' % i], atol=1e-6)
+    # truncation (BASELINE config 5: "5 levels" of the 12 the shipped rule gives at s=8192) and edge counts of
+    # SURVEY a10: nn = 2s, inter_l = 3 s_l - 6 without periodic wrap
+    X5, ei5, _ = graphs.multi_pole_grid1d(torch.zeros(8192), 8192, is_periodic=False, levels=5)
+    assert [x.shape[0] for x in X5] == [8192, 4096, 2048, 1024, 512]
+    assert ei5[0].shape[1] == 2 * 8192 - 2
+    assert [e.shape[1] for e in ei5[1:]] == [3 * n - 6 for n in (8192, 4096, 2048, 1024, 512)]
+
+
 def test_dropin_modules_resolve_like_the_reference_imports(monkeypatch):
     import importlib
     import sys
