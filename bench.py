@@ -100,55 +100,75 @@ class ClockSampler(object):
                     samples=len(sm))
 
 
-def cpu_reference_rate(cfg, seconds_target, steps=1, warmup=0):
-    """Reference CPU path (oracle port) on a bounded sample: out-edges of the first n_s source nodes of the
-    workload graph, T applications.  Returns (edge_apps_per_s, cores, sample_description, ms_per_step)."""
+REF_SAMPLE_SOURCES = 192     # fixed, so that reference-arm numbers are comparable run to run
+
+
+def cpu_reference_rate(cfg, steps=1, warmup=0, n_src=REF_SAMPLE_SOURCES):
+    """The reference's CPU path on a bounded, FIXED sample: out-edges of the first n_src source nodes of the
+    workload graph, T applications of one NNConv.  Runs the reference's OWN files (baseline/_ref, vendored
+    unmodified by oracle/vendor_ref.py; kind 'reference') over oracle/pyg_stub, exactly as the reference runs them
+    (one shot over all edges of the sample, torch CPU fp32); falls back to the oracle port (kind 'port') only when
+    the vendored copy is absent.  Returns (edge_apps_per_s, cores, kind, sample_description, ms_per_step)."""
     from graph_pde_b200 import graphs
     from oracle import nnconv_oracle as O
+    from oracle import vendor_ref
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     s, r, w, kw, T = cfg['s'], cfg['r'], cfg['width'], cfg['ker_width'], cfg['depth']
     n = s * s
+    n_src = min(n, n_src)
     torch.manual_seed(0)
-    ws, bs, root, bias = O.reference_init(w, w, [6, kw, kw, w * w], seed=0)
     grid = graphs.square_grid(s)
     theta = torch.randn(n)
     x = torch.randn(n, w)
+    ei = graphs.ball_connectivity(s, r, 'cpu', True, nodes=(0, n_src))
+    ea = graphs.ball_edge_attr(grid, ei, theta)
+    ref = vendor_ref.import_reference_gno()
+    if ref is not None:
+        ref_nn_conv, ref_util = ref
+        torch.manual_seed(0)
+        kernel = ref_util.DenseNet([6, kw, kw, w * w], torch.nn.ReLU)
+        conv = ref_nn_conv.NNConv_old(w, w, kernel, aggr='mean')
+        kind = 'reference'
 
-    def sample(n_src):
-        ei = graphs.ball_connectivity(s, r, 'cpu', True, nodes=(0, n_src))
-        ea = graphs.ball_edge_attr(grid, ei, theta)
-        return ei, ea
+        def stack():
+            h = x
+            for _ in range(T):                                # UAI1_full_resolution.py:29-30
+                h = torch.relu(conv(h, ei, ea))
+            return h
+    else:
+        ws, bs, root, bias = O.reference_init(w, w, [6, kw, kw, w * w], seed=0)
+        kind = 'port'
 
-    def run(ei, ea):
+        def stack():
+            return O.kernelnn_conv_stack(x, ei, ea, ws, bs, root, bias, T, 'mean')
+
+    def run():
         t0 = time.perf_counter()
         with torch.no_grad():
-            O.kernelnn_conv_stack(x, ei, ea, ws, bs, root, bias, T, 'mean', edge_chunk=8192)
+            stack()
         return time.perf_counter() - t0
 
-    ei, ea = sample(min(n, 64))
-    run(ei, ea)                                   # first-call warm-up (thread pool, allocator)
-    # "all the host threads it can use": more threads than the GEMMs can feed only adds contention on
-    # big boxes, so pick the fastest power-of-two thread count up to the core count on a pilot sample.
-    best = (0.0, cores)
-    cand = sorted({c for c in (cores, 64, 32, 16, 8) if c <= cores}, reverse=True)
-    for c in cand:
-        torch.set_num_threads(c)
-        run(ei, ea)
-        dt = run(ei, ea)
-        if ei.size(1) * T / dt > best[0]:
-            best = (ei.size(1) * T / dt, c)
-    rate, cores = best
     torch.set_num_threads(cores)
-    n_src = int(min(n, max(64, 64 * (rate * seconds_target) / (ei.size(1) * T))))
-    ei, ea = sample(n_src)
+    run()                                         # first-call warm-up (thread pool, allocator)
+    # "all the host threads it can use": more threads than the GEMMs can feed only adds contention on
+    # big boxes, so pick the fastest power-of-two thread count up to the core count on the same sample.
+    best = (float('inf'), cores)
+    for c in sorted({c for c in (cores, 64, 32, 16, 8) if c <= cores}, reverse=True):
+        torch.set_num_threads(c)
+        dt = run()
+        if dt < best[0]:
+            best = (dt, c)
+    cores = best[1]
+    torch.set_num_threads(cores)
     for _ in range(warmup):
-        run(ei, ea)
-    times = [run(ei, ea) for _ in range(max(1, steps))]
+        run()
+    times = [run() for _ in range(max(1, steps))]
     tot = sum(times)
     desc = ('out-edges of the first %d of %d source nodes of the %dx%d r=%g graph (%d edges) x T=%d, fp32, '
-            'torch CPU %d threads, edge_chunk 8192' % (n_src, n, s, s, r, ei.size(1), T, cores))
-    return ei.size(1) * T * len(times) / tot, cores, desc, 1e3 * tot / len(times)
+            'torch CPU %d threads, %s' % (n_src, n, s, s, r, ei.size(1), T, cores,
+                                          "reference's own nn_conv.py + utilities.py over oracle/pyg_stub, one shot"
+                                          if kind == 'reference' else 'oracle port'))
+    return ei.size(1) * T * len(times) / tot, cores, kind, desc, 1e3 * tot / len(times)
 
 
 def gpu_reference_rate(cfg, dev, n_src=2048, chunk=65536):
@@ -188,6 +208,30 @@ def gpu_reference_rate(cfg, dev, n_src=2048, chunk=65536):
                        'edge_chunk %d, one timed pass after one warm-up' % (n_src, ei.size(1), T, chunk))
 
 
+TOL = {'f16': 2e-3, 'bf16': 2e-2, 'f16x2': 2e-5, 'fp32': 2e-5}   # stated tolerances
+
+
+def oracle_stack_cuda(cfg, model, x0, ei, ea, chunk=1 << 16):
+    """The FULL workload graph, all T applications, through the reference-equivalent fp32 torch ops (oracle port,
+    TF32 off) on CUDA tensors, edge-chunked -- the checker for the parity field.  ~30 s at 241^2."""
+    from oracle import nnconv_oracle as O
+    lin = [m for m in model.conv1.nn.layers if isinstance(m, torch.nn.Linear)]
+    ws = [l.weight.detach().float() for l in lin]
+    bs = [l.bias.detach().float() for l in lin]
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            return O.kernelnn_conv_stack(x0, ei, ea, ws, bs, model.conv1.root.detach(), model.conv1.bias.detach(),
+                                         cfg['depth'], 'mean', edge_chunk=chunk)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def rel_err(out, ref):
+    return float((out.double() - ref.double()).abs().max() / ref.double().abs().max().clamp(min=1e-30))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -197,6 +241,7 @@ def main():
     ap.add_argument('--workload', default=os.environ.get('NNCONV_BENCH_WORKLOAD', 'darcy241'), choices=sorted(WORKLOADS))
     ap.add_argument('--precision', default=os.environ.get('NNCONV_B200_PRECISION', 'f16'))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-parity', action='store_true', help='skip the full-graph parity check and the fp32-grade line')
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', '0'))
@@ -213,11 +258,11 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return 0
-        rate, cores, desc, ms = cpu_reference_rate(cfg, 6.0, steps=args.steps, warmup=min(args.warmup, 1))
+        rate, cores, kind, desc, ms = cpu_reference_rate(cfg, steps=args.steps, warmup=min(args.warmup, 1))
         line = dict(metric='NNConv edge-applications/s', value=rate, unit='edge-apps/s', n_gpus=args.gpus,
                     steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling='weak',
                     vs_baseline=None, dtype='f32', data='synthetic', impl='reference', config=config,
-                    cpu_baseline=dict(value=rate, unit='edge-apps/s', cores=cores, kind='port', sample=desc),
+                    cpu_baseline=dict(value=rate, unit='edge-apps/s', cores=cores, kind=kind, sample=desc),
                     e2e=dict(value=rate, unit='edge-apps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                     gpu_launches=0)
         print(json.dumps(line))
@@ -340,10 +385,57 @@ def main():
         prof = {KIND_NAMES[k]: dict(ms=ms_k[k], launches=int(n_k[k])) for k in range(6)}
     barrier()
 
+    # ---- parity at the benchmarked configuration and precision + the fp32-grade (f16x2) line, rank 0 only
+    parity, fp32_grade = None, None
+    if rank == 0 and not args.no_parity:
+        import copy
+        with torch.no_grad():
+            x0 = model.fc1(dev_x[0])
+            got = model.conv_stack(x0, ei, dev_ea[0])
+        model.conv1._h_cache.clear()
+        torch.cuda.empty_cache()
+        ref = oracle_stack_cuda(cfg, model, x0, ei, dev_ea[0])
+        err = rel_err(got, ref)
+        parity = dict(max_rel_err=err, tol=TOL.get(args.precision), ok=bool(err < TOL.get(args.precision, 2e-3)),
+                      vs='oracle port, fp32 torch ops on CUDA (allow_tf32=False), edge-chunked',
+                      config='%s, full graph (E=%d), all T=%d applications, metric max|out-ref|/max|ref| of the final '
+                             'node features' % (args.workload, E, T))
+        del got
+        if args.precision == 'f16':
+            m2 = copy.deepcopy(model)
+            m2.conv1.precision = 'f16x2'
+            m2.conv1.invalidate()
+
+            def step_x2(i):
+                m2.conv1._h_cache.clear()
+                with torch.no_grad():
+                    return m2.conv_stack(m2.fc1(dev_x[i % n_samples]), ei, dev_ea[i % n_samples])
+            st2 = 3
+            for i in range(2):
+                step_x2(i)
+            torch.cuda.synchronize()
+            a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a2.record()
+            for i in range(st2):
+                step_x2(i)
+            b2.record()
+            torch.cuda.synchronize()
+            ms2 = a2.elapsed_time(b2) / st2
+            with torch.no_grad():
+                got2 = m2.conv_stack(x0, ei, dev_ea[0])
+            err2 = rel_err(got2, ref)
+            fp32_grade = dict(precision='f16x2', value=E * T / (ms2 * 1e-3), unit='edge-apps/s', ms_per_step=ms2, steps=st2,
+                              n_gpus=1, parity=dict(max_rel_err=err2, tol=TOL['f16x2'], ok=bool(err2 < TOL['f16x2'])),
+                              note='every tensor-core operand as an fp16 (hi, lo) pair, products hi*hi+hi*lo+lo*hi '
+                                   'in fp32: the like-for-like line against the reference\'s fp32 arithmetic')
+            del got2, m2
+        torch.cuda.empty_cache()
+    barrier()
+
     if rank == 0:
         pk = peaks()
         Kp = ((kw + 63) // 64) * 64
-        es = 4 if args.precision == 'fp32' else 2
+        es = 4 if args.precision in ('fp32', 'f16x2') else 2
         conv_bytes = T * E * (Kp * es + 4)                       # h_e stream + dst index, per step
         gemm_flops = 2.0 * E * Kp * Kp                           # hidden layer 2 (1024 x 1024) per step
         fused = prof['apply_fused']['launches'] > 0
@@ -384,15 +476,18 @@ def main():
                                               'edge-app of the reference formulation; the hoisted/reassociated '
                                               'kernels execute ~40x fewer FLOPs, so formA_tensor_frac may exceed 1'
                                               % (f_alg, b_alg)),
-                    edges=E, nodes=N)
+                    edges=E, nodes=N, parity=parity, fp32_grade=fp32_grade)
         if not args.no_cpu_baseline:
             line['gpu_reference_port'] = gpu_reference_rate(cfg, dev)
-            rate, cores, desc, _ = cpu_reference_rate(cfg, 12.0)
-            line['cpu_baseline'] = dict(value=rate, unit='edge-apps/s', cores=cores, kind='port', sample=desc)
+            rate, cores, kind, desc, _ = cpu_reference_rate(cfg, steps=2)
+            line['cpu_baseline'] = dict(value=rate, unit='edge-apps/s', cores=cores, kind=kind, sample=desc)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not (parity['ok'] and (fp32_grade is None or fp32_grade['parity']['ok'])):
+        sys.stderr.write('bench.py: PARITY FAILED: %s %s\n' % (parity, fp32_grade and fp32_grade['parity']))
+        return 1
     return 0
 
 

@@ -32,7 +32,8 @@ class Data(object):
 
 def collate(items):
     if len(items) == 1:
-        return items[0]
+        # a shallow copy: `batch.to(device)` (UAI1_full_resolution.py:259) must not move the dataset item in place
+        return Data(**{k: getattr(items[0], k) for k in items[0].keys})
     out = Data()
     offset = 0
     offsets = []

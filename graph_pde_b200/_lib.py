@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libnnconv_b200.so')
 CSRC = os.path.join(_HERE, 'csrc')
 
 OK = 0
-PREC = {'fp32': 0, 'f16': 1, 'fp16': 1, 'bf16': 2}
+PREC = {'fp32': 0, 'f16': 1, 'fp16': 1, 'bf16': 2, 'f16x2': 3}
 AGGR = {'add': 0, 'mean': 1}
 FLOW = {'source_to_target': 0, 'target_to_source': 1}
 
@@ -24,6 +24,7 @@ SYMBOLS = [
     'nnconv_edge_features', 'nnconv_apply_sizes', 'nnconv_apply', 'nnconv_gemm_16b',
     'nnconv_profile_begin', 'nnconv_profile_end', 'nnconv_debug_trace_dump',
     'nnconv_backward_sizes', 'nnconv_backward',
+    'nnconv_set_option', 'nnconv_get_option', 'nnconv_edge_features_overflow', 'nnconv_debug_occupy',
 ]
 
 
@@ -81,6 +82,10 @@ def lib():
     L.nnconv_backward.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, P(c_vp), P(c_vp), c_vp, c_vp, c_vp,
                                   c_sz, c_vp]
     L.nnconv_debug_trace_dump.argtypes = [P(ctypes.c_ulonglong), ctypes.c_uint, P(ctypes.c_uint)]
+    L.nnconv_set_option.argtypes = [ctypes.c_char_p, c_int]
+    L.nnconv_get_option.argtypes = [ctypes.c_char_p, P(c_int)]
+    L.nnconv_edge_features_overflow.argtypes = [c_vp, c_vp, P(c_i64)]
+    L.nnconv_debug_occupy.argtypes = [c_int, c_int, ctypes.c_longlong, c_vp]
     for name in SYMBOLS:
         getattr(L, name)
     _lib = L
@@ -91,3 +96,14 @@ def check(status):
     if status != OK:
         msg = lib().nnconv_last_error()
         raise NNConvLibraryError('libnnconv_b200 error %d: %s' % (status, msg.decode() if msg else '?'))
+
+
+def set_option(name, value):
+    """Tuning / debugging knob of the library (csrc/options.h); value=None restores the built-in default."""
+    check(lib().nnconv_set_option(name.encode(), -2000000 if value is None else int(value)))
+
+
+def get_option(name):
+    v = ctypes.c_int(0)
+    check(lib().nnconv_get_option(name.encode(), ctypes.byref(v)))
+    return v.value

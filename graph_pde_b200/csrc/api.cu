@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "options.h"
 
 namespace nnc {
 
@@ -51,7 +52,7 @@ struct WeightsLayout {
 
 static int fill_dims(Weights* W, int n_layers, const int* dims, int cin, int cout, int prec) {
   NNC_REQUIRE(n_layers >= 1 && n_layers <= kMaxLayers, NNCONV_ERR_ARG, "edge MLP must have 1..%d Linear layers", kMaxLayers);
-  NNC_REQUIRE(prec >= PREC_FP32 && prec <= PREC_BF16, NNCONV_ERR_ARG, "unknown precision %d", prec);
+  NNC_REQUIRE(prec >= PREC_FP32 && prec <= PREC_F16X2, NNCONV_ERR_ARG, "unknown precision %d", prec);
   NNC_REQUIRE(cin >= 1 && cout >= 1, NNCONV_ERR_ARG, "bad channel counts");
   NNC_REQUIRE(dims[n_layers] == cin * cout, NNCONV_ERR_ARG,
               "edge MLP output width %d != in_channels*out_channels = %d", dims[n_layers], cin * cout);
@@ -68,7 +69,12 @@ static int fill_dims(Weights* W, int n_layers, const int* dims, int cin, int cou
   W->K = dims[n_layers - 1];
   W->Kp = round_up(W->K, 64);
   W->prec = prec;
+  W->split = prec_is_split(prec) ? 1 : 0;
   W->esize = esize_of(prec);
+  if (W->split) {
+    NNC_REQUIRE(n_layers >= 2 && 3 * dims[0] + 2 <= 64, NNCONV_ERR_UNSUPPORTED,
+                "precision f16x2 needs an edge MLP with >= 2 Linear layers and k_in <= 20 (tensor-core first layer)");
+  }
   return NNCONV_OK;
 }
 
@@ -82,10 +88,10 @@ static WeightsLayout layout_weights(const Weights* W) {
     L.off_W1aug = c.off; c.take<char>(static_cast<size_t>(W->kp[1]) * 64 * 2);
   }
   for (int l = 2; l <= nl - 1; ++l) {
-    L.off_Wh[l] = c.off; c.take<char>(static_cast<size_t>(W->kp[l]) * W->kp[l - 1] * W->esize);
+    L.off_Wh[l] = c.off; c.take<char>(static_cast<size_t>(W->kp[l]) * W->kp[l - 1] * W->esize * (W->split ? 3 : 1));
     L.off_bh[l] = c.off; c.take<float>(W->kp[l]);
   }
-  L.off_W3p = c.off; c.take<char>(static_cast<size_t>(W->cout) * W->Kp * W->cin_p * W->esize);
+  L.off_W3p = c.off; c.take<char>(static_cast<size_t>(W->cout) * W->Kp * W->cin_p * W->esize * (W->split ? 3 : 1));
   L.off_B3 = c.off; c.take<float>(static_cast<size_t>(W->cin) * W->cout);
   L.bytes = c.off;
   return L;
@@ -152,58 +158,53 @@ static int max_hidden_kp(const Weights* W) {
   return m;
 }
 
-// How the first two layers run: 0 = two GEMM kernels (h1 through HBM), 1 = on-chip fusion (mlp_fused_tc.cu,
-// experimental), 2 = two pipelines meeting in an L2 ring (mlp_ring_tc.cu).  NNCONV_MLP12 = split | onchip | ring.
-static int ef_mlp12_mode(const Weights* W) {
-  if (W->W1aug == nullptr || W->n_layers < 3) return 0;
-  const char* e = getenv("NNCONV_MLP12");
-  if (e != nullptr) {
-    if (strcmp(e, "ring") == 0) return 2;
-    if (strcmp(e, "onchip") == 0) return 1;
-    if (strcmp(e, "split") == 0) return 0;
-  }
-  const char* f = getenv("NNCONV_FUSE12");
-  if (f != nullptr && atoi(f) > 0) return 1;
-  return 0;
-}
-
-static bool ef_fuse12(const Weights* W) {
-  return ef_mlp12_mode(W) != 0;
-}
+constexpr size_t kEfHeader = 1024;   // start of the edge-feature workspace: [0] = overflow counter (int)
 
 static size_t ef_row_bytes(const Weights* W) {
   // per edge row of workspace: A1 (64 x 16-bit, tensor-core first layer) + ping/pong hidden activations
+  // (PREC_F16X2: [hi | lo] pairs, twice the width)
   size_t row = 0;
   if (W->W1aug) row += 128;
-  const bool fuse = ef_fuse12(W);
-  if (W->n_layers > (fuse ? 3 : 2)) row += 2 * static_cast<size_t>(max_hidden_kp(W)) * W->esize;
+  if (W->n_layers > 2) row += 2 * static_cast<size_t>(max_hidden_kp(W)) * W->esize * (W->split ? 2 : 1);
   return row;
 }
 
 size_t edge_features_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes) {
   const size_t row = ef_row_bytes(W);
-  if (row == 0) return 1024;   // h_last is written directly by the CUDA-core first-layer kernel
+  if (row == 0) return kEfHeader + 1024;   // h_last is written directly by the CUDA-core first-layer kernel
   size_t rows_all = static_cast<size_t>(round_up64(P->E > 0 ? P->E : 1, 128));
   size_t rows = want_bytes / row;
   rows = rows / 128 * 128;
   if (rows < 128) rows = 128;
   if (rows > rows_all) rows = rows_all;
-  size_t ring = 0;
-  if (ef_mlp12_mode(W) == 2) ring = static_cast<size_t>(round_up64(static_cast<int64_t>(mlp_ring_bytes(W->kp[1])), 1024));
-  return ring + rows * row + 8192;
+  return kEfHeader + rows * row + 8192;
 }
 
 int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void* h, void* ws, size_t ws_bytes,
                   cudaStream_t st, int64_t* launches) {
   const int64_t E = P->E;
+  NNC_REQUIRE(ws != nullptr && ws_bytes >= kEfHeader, NNCONV_ERR_WORKSPACE, "edge_features: workspace too small");
+  int* overflow = static_cast<int*>(ws);
+  NNC_CHECK_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), st));
   if (E == 0) return NNCONV_OK;
+  if (!options().overflow_check) overflow = nullptr;
+  ws = static_cast<char*>(ws) + kEfHeader;
+  ws_bytes -= kEfHeader;
   const int nl = W->n_layers;
   const bool tc = tc_shapes_supported(W);
   NNC_REQUIRE(tc || W->prec == PREC_FP32, NNCONV_ERR_UNSUPPORTED,
               "shape not supported by the tensor-core path (out=%d, K=%d); use precision fp32", W->cout, W->K);
   int s;
-  // 16-bit path: h is chunk-major [Kp/64][E_pad][64] (what the contraction kernel streams); fp32: row-major
+  const int amul = W->split ? 2 : 1;   // activation width multiplier ([hi | lo])
+  const int kmul = W->split ? 3 : 1;   // GEMM K multiplier ([hi | hi | lo] x [hi | lo | hi])
+  // 16-bit path: h is chunk-major [amul*Kp/64][E_pad][64] (what the contraction kernel streams); fp32: row-major
   const int64_t hpad = W->prec == PREC_FP32 ? 0 : round_up64(E, 128);
+  if (hpad > E) {
+    // rows [E, E_pad) of every panel are read (never used) by TMA boxes that run past the last edge; the backward
+    // multiplies them by zero, so they must not hold NaN bit patterns of a recycled allocation
+    NNC_CHECK_CUDA(cudaMemset2DAsync(static_cast<char*>(h) + static_cast<size_t>(E) * 128, static_cast<size_t>(hpad) * 128,
+                                     0, static_cast<size_t>(hpad - E) * 128, static_cast<size_t>(amul * W->Kp / 64), st));
+  }
   if (nl == 1) {   // single Linear: h_last = edge_attr (padded)
     ProfScope ps(PK_LAYER1, st);
     s = launch_edge_layer1(W->prec, edge_attr, P->perm, 0, E, W->dims[0], nullptr, nullptr, W->Kp, 1, h, st, hpad, 0);
@@ -217,21 +218,9 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
     if (launches) ++*launches;
     return s;
   }
-  const int mlp12 = ef_mlp12_mode(W);
-  const bool fuse12 = mlp12 != 0;
-  size_t ring_bytes = 0;
-  char* ring = nullptr;
-  if (mlp12 == 2) {    // the per-CTA h1 ring sits at the start of the workspace
-    ring_bytes = static_cast<size_t>(round_up64(static_cast<int64_t>(mlp_ring_bytes(W->kp[1])), 1024));
-    NNC_REQUIRE(ws != nullptr && ws_bytes > ring_bytes + 128 * rowb + 4096, NNCONV_ERR_WORKSPACE,
-                "edge_features: workspace too small for the h1 ring");
-    ring = static_cast<char*>(ws);
-    ws = ring + ring_bytes;
-    ws_bytes -= ring_bytes;
-  }
-  NNC_REQUIRE(ws != nullptr && ws_bytes >= 128 * rowb + 4096, NNCONV_ERR_WORKSPACE, "edge_features: workspace too small");
+  NNC_REQUIRE(ws_bytes >= 128 * rowb + 4096, NNCONV_ERR_WORKSPACE, "edge_features: workspace too small");
   const int64_t rows = static_cast<int64_t>((ws_bytes - 4096) / rowb) / 128 * 128;
-  const size_t hid = static_cast<size_t>(max_hidden_kp(W)) * W->esize;
+  const size_t hid = static_cast<size_t>(max_hidden_kp(W)) * W->esize * amul;
   char* a1 = static_cast<char*>(ws);
   char* bufA = a1 + (W->W1aug ? round_up64(rows * 128, 1024) : 0);
   char* bufB = bufA + round_up64(static_cast<int64_t>(rows * hid), 1024);
@@ -240,33 +229,14 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
     void* h_rows = hpad > 0 ? h : static_cast<void*>(static_cast<char*>(h) + static_cast<size_t>(e0) * W->Kp * W->esize);
     const int64_t h_pad_l1 = nl == 2 ? hpad : 0;     // first layer writes h directly only for 2-layer MLPs
     void* dst1 = nl == 2 ? h_rows : static_cast<void*>(bufA);
-    int first_hidden = 2;
-    if (fuse12) {   // layers 1+2 fused: A1 -> (h1 on chip) -> h2
-      {
-        ProfScope ps(PK_LAYER1, st);
-        s = launch_build_a1(W->prec, edge_attr, P->perm, e0, n, W->dims[0], a1, st);
-      }
-      if (s) return s;
-      const bool last2 = nl == 3;
-      {
-        ProfScope ps(PK_HIDDEN_GEMM, st);
-        if (mlp12 == 2)
-          s = launch_mlp_ring_tc(W->prec, a1, n, W->dims[0], W->W1aug, W->kp[1], W->Wh[2], W->kp[2], W->bh[2], ring,
-                                 last2 ? h_rows : static_cast<void*>(bufA), W->kp[2], last2 ? hpad : 0, e0, st);
-        else
-          s = launch_mlp12_tc(W->prec, a1, n, W->dims[0], W->W1aug, W->kp[1], W->Wh[2], W->kp[2], W->bh[2],
-                              last2 ? h_rows : static_cast<void*>(bufA), W->kp[2], last2 ? hpad : 0, e0, st);
-      }
-      if (s) return s;
-      if (launches) *launches += 2;
-      first_hidden = 3;
-    } else {
+    {
       ProfScope ps(PK_LAYER1, st);
       if (W->W1aug) {
         s = launch_build_a1(W->prec, edge_attr, P->perm, e0, n, W->dims[0], a1, st);
         if (s) return s;
         s = launch_gemm_tc(W->prec, a1, n, 0, static_cast<int>(n), 64, W->W1aug, W->kp[1], nullptr, 1, dst1,
-                           W->kp[1], st, nullptr, h_pad_l1, e0);
+                           static_cast<int64_t>(amul) * W->kp[1], st, nullptr, h_pad_l1, e0,
+                           W->split ? GEMM_C_SPLIT : 0, overflow);
         if (launches) ++*launches;
       } else {
         s = launch_edge_layer1(W->prec, edge_attr, P->perm, e0, n, W->dims[0], W->W1, W->b1, W->kp[1], 0, dst1, st,
@@ -274,10 +244,10 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
       }
     }
     if (s) return s;
-    if (launches && !fuse12) ++*launches;
+    if (launches) ++*launches;
     char* cur = bufA;
     char* nxt = bufB;
-    for (int l = first_hidden; l <= nl - 1; ++l) {
+    for (int l = 2; l <= nl - 1; ++l) {
       const bool last = l == nl - 1;
       void* dst = last ? h_rows : static_cast<void*>(nxt);
       ProfScope ps(PK_HIDDEN_GEMM, st);
@@ -286,8 +256,9 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
                                reinterpret_cast<const float*>(W->Wh[l]), W->kp[l - 1], static_cast<float*>(dst),
                                W->kp[l], static_cast<int>(n), W->kp[l], W->kp[l - 1], W->bh[l], st);
       } else {
-        s = launch_gemm_tc(W->prec, cur, n, 0, static_cast<int>(n), W->kp[l - 1], W->Wh[l], W->kp[l], W->bh[l], 1,
-                           dst, W->kp[l], st, nullptr, last ? hpad : 0, e0);
+        s = launch_gemm_tc(W->prec, cur, n, 0, static_cast<int>(n), kmul * W->kp[l - 1], W->Wh[l], W->kp[l], W->bh[l], 1,
+                           dst, static_cast<int64_t>(amul) * W->kp[l], st, nullptr, last ? hpad : 0, e0,
+                           W->split ? (GEMM_A_SPLIT | GEMM_C_SPLIT) : 0, overflow);
       }
       if (s) return s;
       if (launches) ++*launches;
@@ -309,13 +280,13 @@ static ApplyLayout layout_apply(const Plan* P, const Weights* W) {
   Carver c(nullptr, ~size_t(0));
   ApplyLayout L{};
   const size_t S = P->n_src > 0 ? P->n_src : 1;
-  L.off_Xc = c.off; c.take<char>((S + 128) * W->cin_p * W->esize);
+  L.off_Xc = c.off; c.take<char>((S + 128) * W->cin_p * W->esize * (W->split ? 3 : 1));
   L.off_cvec = c.off; c.take<float>(S * W->cout);
   L.off_xs = c.off; c.take<float>(S);
   L.off_flags = c.off; c.take<int>(5 * kMaxPipeBatches);
   L.off_Y = c.off;
   L.fixed_bytes = c.off;
-  L.per_node = static_cast<size_t>(W->cout) * W->Kp * W->esize;
+  L.per_node = static_cast<size_t>(W->cout) * W->Kp * W->esize * (W->split ? 2 : 1);
   return L;
 }
 
@@ -384,10 +355,10 @@ int apply(const Plan* P, const Weights* W, const void* h, const float* x, const 
 
   // Tensor-core path, default: ONE persistent kernel per application (apply_tc.cu) in which every CTA runs
   // the Y GEMM pipeline and the contraction pipeline concurrently over a ring of L2-resident Y batches.
-  const bool no_fuse_env = getenv("NNCONV_NO_FUSE") != nullptr;      // measurement / debugging knob
+  const Options& opt = options();
+  const bool no_fuse_env = opt.no_fuse != 0 && !W->split;      // measurement / debugging knob
   if (!no_fuse_env && apply_fused_supported(W)) {
-    int ring = 3;   // measured (run22): with dynamic unit scheduling 3 x 128 sources (48 MB at out=64, Kp=1024) is best
-    if (const char* e = getenv("NNCONV_RING")) { int v = atoi(e); if (v >= 2 && v <= 8) ring = v; }
+    int ring = opt.ring;   // measured (run22): with dynamic unit scheduling 3 x 128 sources (48 MB at out=64, Kp=1024) is best
     if (nodes_cap < ring) ring = nodes_cap >= 2 ? static_cast<int>(nodes_cap) : 1;
     int64_t nb = nodes_cap / ring;
     if (nb >= 128) nb = nb / 128 * 128;
@@ -400,11 +371,16 @@ int apply(const Plan* P, const Weights* W, const void* h, const float* x, const 
         s = launch_apply_tc(W->prec, P, W, h, Xc, Y, static_cast<int>(nb), ring, cvec, xs, aggr_mean, out, flags,
                             kMaxPipeBatches, st);
       }
-      if (s) return s;
-      if (launches) ++*launches;
-      return NNCONV_OK;
+      if (s == NNCONV_OK) {
+        if (launches) ++*launches;
+        return NNCONV_OK;
+      }
+      // the driver cannot co-schedule one CTA per SM (MPS / green-context partition): per-batch kernels below
+      if (s != kApplyCannotCoSchedule) return s;
     }
   }
+  NNC_REQUIRE(!W->split, NNCONV_ERR_UNSUPPORTED,
+              "precision f16x2 runs in the fused persistent kernel only (shape or workspace not supported)");
 
   // Fallback (NNCONV_NO_FUSE=1 or shapes the fused kernel does not cover): one Y GEMM + one contraction
   // kernel per batch of sources.  Batches of sources sized so that the Y buffers stay L2 resident; kernel order
@@ -413,7 +389,7 @@ int apply(const Plan* P, const Weights* W, const void* h, const float* x, const 
   // the running kernel retire; the true dependencies  C(b) <- Y(b)  and  Y(b) <- C(b-3) (buffer reuse)
   // are completion flags in global memory.  Profiling mode (events between kernels) falls back to plain
   // stream order so that per-kernel times are meaningful.
-  const bool no_pipe_env = getenv("NNCONV_NO_PIPE") != nullptr;   // measurement / debugging knob
+  const bool no_pipe_env = opt.no_pipe != 0;   // measurement / debugging knob
   const bool pipe = !prof_enabled() && !no_pipe_env && nodes_cap >= 3;
   int64_t nb_max = pipe ? nodes_cap / 3 : nodes_cap;
   if (nb_max > P->n_src) nb_max = P->n_src;
@@ -496,7 +472,21 @@ const char* nnconv_last_error(void) { return nnc::g_err; }
 
 int nnconv_abi_version(void) { return NNCONV_B200_ABI_VERSION; }
 
-int nnconv_init(void) { return tc_init(); }
+int nnconv_init(void) {
+  (void)nnc::options();   // read the NNCONV_* environment once
+  return tc_init();
+}
+
+int nnconv_set_option(const char* name, int value) {
+  NNC_REQUIRE(name != nullptr && nnc::option_set(name, value) == 0, NNCONV_ERR_ARG, "unknown option '%s'", name ? name : "");
+  return NNCONV_OK;
+}
+
+int nnconv_get_option(const char* name, int* value) {
+  NNC_REQUIRE(name != nullptr && value != nullptr && nnc::option_get(name, value) == 0, NNCONV_ERR_ARG,
+              "unknown option '%s'", name ? name : "");
+  return NNCONV_OK;
+}
 
 int nnconv_plan_sizes(int64_t E, int64_t N, size_t* ws_bytes, size_t* tmp_bytes) {
   NNC_REQUIRE(ws_bytes && tmp_bytes, NNCONV_ERR_ARG, "null output pointer");
@@ -587,7 +577,7 @@ int nnconv_edge_features_sizes(const nnconv_plan_t* plan, const nnconv_weights_t
                                size_t* h_bytes, size_t* ws_bytes) {
   NNC_REQUIRE(plan && w && h_bytes && ws_bytes, NNCONV_ERR_ARG, "null pointer");
   const int64_t rows = round_up64(plan->p.E > 0 ? plan->p.E : 1, 128);
-  *h_bytes = static_cast<size_t>(rows) * w->w.Kp * w->w.esize;
+  *h_bytes = static_cast<size_t>(rows) * w->w.Kp * w->w.esize * (w->w.split ? 2 : 1);
   *ws_bytes = edge_features_ws_bytes(&plan->p, &w->w, want_ws_bytes);
   return NNCONV_OK;
 }
@@ -596,6 +586,16 @@ int nnconv_edge_features(const nnconv_plan_t* plan, const nnconv_weights_t* w, c
                          void* ws, size_t ws_bytes, void* stream, int64_t* launches) {
   NNC_REQUIRE(plan && w && (edge_attr || plan->p.E == 0) && h, NNCONV_ERR_ARG, "null pointer");
   return edge_features(&plan->p, &w->w, edge_attr, h, ws, ws_bytes, static_cast<cudaStream_t>(stream), launches);
+}
+
+int nnconv_edge_features_overflow(const void* ws, void* stream, int64_t* count) {
+  NNC_REQUIRE(ws && count, NNCONV_ERR_ARG, "null pointer");
+  int v = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  NNC_CHECK_CUDA(cudaMemcpyAsync(&v, ws, sizeof(int), cudaMemcpyDeviceToHost, st));
+  NNC_CHECK_CUDA(cudaStreamSynchronize(st));
+  *count = v;
+  return NNCONV_OK;
 }
 
 int nnconv_apply_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t want_y_bytes, size_t* ws_bytes) {
@@ -657,6 +657,29 @@ int nnconv_profile_end(double* ms_by_kind, int64_t* launches_by_kind, int n_kind
 int nnconv_debug_trace_dump(unsigned long long* host_rec, unsigned int max_rec, unsigned int* n_out) {
   NNC_REQUIRE(host_rec && n_out, NNCONV_ERR_ARG, "null pointer");
   return trace_dump(host_rec, max_rec, n_out);
+}
+
+// test hook: `n_ctas` CTAs that each hold `smem_bytes` of shared memory and spin for `ns` nanoseconds
+__global__ void k_debug_occupy(long long ns) {
+  extern __shared__ char occ_smem[];
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  occ_smem[threadIdx.x] = 0;
+  for (;;) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (static_cast<long long>(t - t0) >= ns) break;
+    __nanosleep(1000);
+  }
+}
+
+int nnconv_debug_occupy(int n_ctas, int smem_bytes, long long ns, void* stream) {
+  NNC_REQUIRE(n_ctas >= 1 && smem_bytes >= 0 && smem_bytes <= 227 * 1024 && ns >= 0 && ns <= 2000000000ll, NNCONV_ERR_ARG,
+              "debug_occupy: bad arguments");
+  NNC_CHECK_CUDA(cudaFuncSetAttribute(k_debug_occupy, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  k_debug_occupy<<<n_ctas, 128, smem_bytes, static_cast<cudaStream_t>(stream)>>>(ns);
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
 }
 
 int nnconv_gemm_16b(int precision, const void* A, int64_t M, int K, const void* B, int N, const float* bias,

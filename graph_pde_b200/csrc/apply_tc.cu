@@ -15,9 +15,8 @@
 //                      okC[b]  raised when all grid CTAs consumed batch b                 (Y waits okC[b-ring])
 //
 // Math and data movement of the two pipelines are those of conv_tc.cu and gemm_tc.cu.
-#include <cstdlib>
-
 #include "kernels.h"
+#include "options.h"
 #include "tc05.cuh"
 #include "tmap.h"
 
@@ -53,6 +52,10 @@ struct ApplyArgs {
   float* out;             // [N, cout]
   int n_src, nb, n_batches, ring;
   int cout, nb_slots, passes, a_stages, e_pad;
+  // PREC_F16X2 (plan.h): split_nk = Kp/64 > 0 -> h holds 2*split_nk chunk panels [hi | lo], a Y ring row is
+  // [cout][hi(Kp) | lo(Kp)], and contraction step j = 3q + r pairs (A, B) = (hi_q, Yhi_q), (hi_q, Ylo_q), (lo_q, Yhi_q)
+  int split_nk;
+  int Kp;
   // Y GEMM
   int NY;                 // cout * Kp
   int num_kx;             // cin_p / 64
@@ -213,10 +216,16 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
       // only nb_slots chunks later, i.e. 2*nb_slots - 1 MMA blocks for a 2-tile unit (with a pass-major order it
       // was nb_slots - 1 and the MMA warp spent 20% of its time waiting for B, ncu r1g)
       for (int j = 0; j < num_kc; ++j) {
+        int ja = j, jb = j;
+        if (a.split_nk > 0) {
+          const int q = j / 3, r = j - 3 * q;
+          ja = r == 2 ? a.split_nk + q : q;
+          jb = r == 1 ? a.split_nk + q : q;
+        }
         mbar_wait(&b_empty[bs], bph ^ 1u);
         if (elect_one()) {
           mbar_arrive_expect_tx(&b_full[bs], b_chunk_bytes);
-          tma_load_2d(smem_b + bs * b_stride, &tmY, &b_full[bs], j * 64, (ring_row0 + uc) * a.cout, kEvictLast);
+          tma_load_2d(smem_b + bs * b_stride, &tmY, &b_full[bs], jb * 64, (ring_row0 + uc) * a.cout, kEvictLast);
         }
         __syncwarp();
         if (++bs == a.nb_slots) { bs = 0; bph ^= 1u; }
@@ -228,7 +237,7 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
             mbar_wait(&a_empty[stage], phase ^ 1u);
             if (elect_one()) {
               mbar_arrive_expect_tx(&a_full[stage], a_bytes);
-              tma_load_2d(smem_a + stage * kATileBytes, mh, &a_full[stage], 0, j * a.e_pad + te0[ti], kEvictFirst);
+              tma_load_2d(smem_a + stage * kATileBytes, mh, &a_full[stage], 0, ja * a.e_pad + te0[ti], kEvictFirst);
             }
             __syncwarp();
             if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
@@ -432,7 +441,8 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
         named_bar_sync(2, 128);
       }
       const unsigned long long ty1 = a.trace.rec ? gtime() : 0ull;
-      uint16_t* ybase = reinterpret_cast<uint16_t*>(a.Yring) + static_cast<int64_t>(b % a.ring) * a.nb * a.NY;
+      const int ymul = a.split_nk > 0 ? 2 : 1;
+      uint16_t* ybase = reinterpret_cast<uint16_t*>(a.Yring) + static_cast<int64_t>(b % a.ring) * a.nb * a.NY * ymul;
       for (int i = static_cast<int>((blockIdx.x + 7u * b) % gridDim.x); i < tiles; i += gridDim.x, ++it) {
         const int mb = i / n_blocks, nbk = i % n_blocks;
         const int ys = it & 1;
@@ -440,7 +450,9 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
         fence_after_sync();
         const int row = mb * 128 + quarter * 32 + lane;
         const bool row_ok = row < rows;
-        uint16_t* yrow = ybase + static_cast<int64_t>(row) * a.NY + nbk * kYBlockN;
+        // column n = o * Kp + k of the source's matrix; with split rows of 2*Kp: offset n + o * Kp
+        const int n0 = nbk * kYBlockN;
+        uint16_t* yrow0 = ybase + static_cast<int64_t>(row) * a.NY * ymul;
         const uint32_t tb = tmem_y + (static_cast<uint32_t>(quarter * 32) << 16) + ys * kYBlockN;
         uint32_t v[2][32];
         tmem_ld32(tb, v[0]);
@@ -450,20 +462,31 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
           if (cc + 1 < kYBlockN / 32) tmem_ld32(tb + (cc + 1) * 32, v[(cc + 1) & 1]);
           if (row_ok) {
             const uint32_t* vv = v[cc & 1];
-            uint32_t packed[16];
+            uint32_t packed[16], packed_lo[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const float f0 = __uint_as_float(vv[2 * j]), f1 = __uint_as_float(vv[2 * j + 1]);
               if (FMT == 0) {
                 __half2 hh = __floats2half2_rn(f0, f1);
                 packed[j] = *reinterpret_cast<uint32_t*>(&hh);
+                if (a.split_nk > 0) {
+                  const float2 hf = __half22float2(hh);
+                  __half2 ll = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
+                  packed_lo[j] = *reinterpret_cast<uint32_t*>(&ll);
+                }
               } else {
                 __nv_bfloat162 hh = __floats2bfloat162_rn(f0, f1);
                 packed[j] = *reinterpret_cast<uint32_t*>(&hh);
               }
             }
-            st_global_v8_hint(yrow + cc * 32, packed, a.y_store_policy);
-            st_global_v8_hint(yrow + cc * 32 + 16, packed + 8, a.y_store_policy);
+            const int n = n0 + cc * 32;
+            uint16_t* yrow = yrow0 + n + (a.split_nk > 0 ? (n / a.Kp) * a.Kp : 0);
+            st_global_v8_hint(yrow, packed, a.y_store_policy);
+            st_global_v8_hint(yrow + 16, packed + 8, a.y_store_policy);
+            if (FMT == 0 && a.split_nk > 0) {
+              st_global_v8_hint(yrow + a.Kp, packed_lo, a.y_store_policy);
+              st_global_v8_hint(yrow + a.Kp + 16, packed_lo + 8, a.y_store_policy);
+            }
           }
           if (cc + 1 < kYBlockN / 32) tmem_ld_wait();
         }
@@ -525,42 +548,89 @@ bool apply_shape(int cout, int Kp, int ybn, ApplyShape* as) {
 static int y_block_n() {
   // N tile of the Y pipeline: 64 (default: smaller stage -> 7 instead of 6 A stages for the h stream, measured
   // 72.6 vs 74.1 ms per step at 241^2, run27) or 128
-  if (const char* e = getenv("NNCONV_Y_BLOCKN")) return atoi(e) == 128 ? 128 : 64;
-  return 64;
+  return options().y_block_n == 128 ? 128 : 64;
 }
 
+static int eff_kp(const Weights* W) { return W->split ? 3 * W->Kp : W->Kp; }
+
 bool apply_fused_supported(const Weights* W) {
-  if (W->prec != PREC_F16 && W->prec != PREC_BF16) return false;
+  if (W->prec != PREC_F16 && W->prec != PREC_BF16 && W->prec != PREC_F16X2) return false;
   if ((W->cout * W->Kp) % 128 != 0) return false;
   ApplyShape as;
-  return apply_shape(W->cout, W->Kp, y_block_n(), &as);
+  return apply_shape(W->cout, eff_kp(W), y_block_n(), &as);
 }
+
+namespace {
+template <int FMT, int YBN>
+int launch_variant(int grid, int smem_bytes, bool coop, cudaStream_t st, const HMaps& tmH, const CUtensorMap& tmY,
+                   const CUtensorMap& tmX, const CUtensorMap& tmW, const ApplyArgs& a) {
+  static bool attr_set = false;
+  static int blocks_per_sm = -1;
+  if (!attr_set) {
+    NNC_CHECK_CUDA(cudaFuncSetAttribute(k_apply_tc<FMT, YBN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  if (blocks_per_sm < 0)
+    NNC_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_apply_tc<FMT, YBN>, kThreads,
+                                                                 smem_bytes));
+  NNC_REQUIRE(blocks_per_sm >= 1, NNCONV_ERR_UNSUPPORTED, "apply_tc: the persistent kernel does not fit one SM");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  // The CTAs of this kernel wait for each other (okY / okC flags), so ALL of them must be resident at the same
+  // time.  A cooperative launch makes the driver guarantee exactly that: it only starts the grid once every CTA
+  // can be co-scheduled, whatever else (an overlapped NCCL kernel, a second stream, MPS) holds SMs right now,
+  // and fails with cudaErrorCooperativeLaunchTooLarge when that can never happen -- the caller then falls back
+  // to the per-batch kernels, which need no co-residency.
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = coop ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_apply_tc<FMT, YBN>, tmH, tmY, tmX, tmW, a);
+  if (e == cudaErrorCooperativeLaunchTooLarge) {
+    cudaGetLastError();
+    return kApplyCannotCoSchedule;   // handled by apply(): per-batch kernels instead
+  }
+  NNC_CHECK_CUDA(e);
+  return NNCONV_OK;
+}
+}  // namespace
 
 int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, const void* Xc, void* Yring, int nb,
                     int ring, const float* cvec, const float* xs, int aggr_mean, float* out, int* flags,
                     int flags_stride, cudaStream_t st) {
   int s = tc_init();
   if (s != NNCONV_OK) return s;
+  const Options& opt = options();
   const int bf = prec == PREC_BF16;
+  const int split = W->split ? 1 : 0;
   const int ybn = y_block_n();
   ApplyShape as;
-  NNC_REQUIRE(apply_shape(W->cout, W->Kp, ybn, &as), NNCONV_ERR_UNSUPPORTED, "apply_tc: unsupported shape");
-  if (const char* e = getenv("NNCONV_APPLY_STAGES")) { int v = atoi(e); if (v >= 2 && v < as.a_stages) as.a_stages = v; }
+  NNC_REQUIRE(apply_shape(W->cout, eff_kp(W), ybn, &as), NNCONV_ERR_UNSUPPORTED, "apply_tc: unsupported shape");
+  if (opt.apply_stages >= 2 && opt.apply_stages < as.a_stages) as.a_stages = opt.apply_stages;
   const int64_t e_pad = round_up64(P->E, 128);
   const int NY = W->cout * W->Kp;
+  const int kmul = split ? 2 : 1;      // [hi | lo] activations / Y rows
+  const int xmul = split ? 3 : 1;      // [hi | hi | lo] x [hi | lo | hi] operands of the Y GEMM
   const int n_batches = ceil_div(P->n_src, nb);
   NNC_REQUIRE(n_batches <= flags_stride, NNCONV_ERR_WORKSPACE, "apply_tc: too many source batches (%d)", n_batches);
+  NNC_REQUIRE(static_cast<uint64_t>(kmul * W->Kp / 64) * e_pad < (1ull << 31), NNCONV_ERR_UNSUPPORTED,
+              "apply_tc: edge-feature tensor exceeds 2^31 rows of 64 columns");
   HMaps tmH;
   CUtensorMap tmY, tmX, tmW;
   for (int i = 0; i < 8; ++i) {
-    s = make_tmap_2d_16b(&tmH.m[i], bf, h, static_cast<uint64_t>(W->Kp / 64) * e_pad, 64, 16 * (i + 1));
+    s = make_tmap_2d_16b(&tmH.m[i], bf, h, static_cast<uint64_t>(kmul * W->Kp / 64) * e_pad, 64, 16 * (i + 1));
     if (s != NNCONV_OK) return s;
   }
-  s = make_tmap_2d_16b(&tmY, bf, Yring, static_cast<uint64_t>(ring) * nb * W->cout, static_cast<uint64_t>(W->Kp), W->cout);
+  s = make_tmap_2d_16b(&tmY, bf, Yring, static_cast<uint64_t>(ring) * nb * W->cout, static_cast<uint64_t>(kmul) * W->Kp,
+                       W->cout);
   if (s != NNCONV_OK) return s;
-  s = make_tmap_2d_16b(&tmX, bf, Xc, static_cast<uint64_t>(P->n_src), static_cast<uint64_t>(W->cin_p), 128);
+  s = make_tmap_2d_16b(&tmX, bf, Xc, static_cast<uint64_t>(P->n_src), static_cast<uint64_t>(xmul) * W->cin_p, 128);
   if (s != NNCONV_OK) return s;
-  s = make_tmap_2d_16b(&tmW, bf, W->W3p, static_cast<uint64_t>(NY), static_cast<uint64_t>(W->cin_p), ybn);
+  s = make_tmap_2d_16b(&tmW, bf, W->W3p, static_cast<uint64_t>(NY), static_cast<uint64_t>(xmul) * W->cin_p, ybn);
   if (s != NNCONV_OK) return s;
   ApplyArgs a;
   a.tile_c = P->tile_c; a.tile_e0 = P->tile_e0; a.tile_cnt = P->tile_cnt; a.tile_ptr = P->tile_ptr;
@@ -569,67 +639,54 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
   a.n_src = P->n_src; a.nb = nb; a.n_batches = n_batches; a.ring = ring;
   a.cout = W->cout; a.nb_slots = as.nb_slots; a.passes = as.passes; a.a_stages = as.a_stages;
   a.e_pad = static_cast<int>(e_pad);
-  a.NY = NY; a.num_kx = W->cin_p / 64; a.Yring = Yring;
-  a.y_store_policy = kEvictNormal;
-  a.debug_scatter = 0;
-  if (const char* e = getenv("NNCONV_DEBUG_SCATTER")) a.debug_scatter = atoi(e);   // wrong results, timing only
-  if (const char* e = getenv("NNCONV_Y_STORE_POLICY")) a.y_store_policy = atoi(e) == 1 ? kEvictLast : atoi(e) == 2 ? kEvictFirst : kEvictNormal;
+  a.split_nk = split ? W->Kp / 64 : 0;
+  a.Kp = W->Kp;
+  a.NY = NY; a.num_kx = xmul * W->cin_p / 64; a.Yring = Yring;
+  a.y_store_policy = opt.y_store_policy == 1 ? kEvictLast : opt.y_store_policy == 2 ? kEvictFirst : kEvictNormal;
+  a.debug_scatter = opt.debug_scatter;   // wrong results, timing only
   a.cntY = flags; a.cntC = flags + flags_stride; a.okY = flags + 2 * flags_stride; a.okC = flags + 3 * flags_stride;
   a.cntU = flags + 4 * flags_stride;
   {
     TraceHandle th = trace_get();
     a.trace = TraceBuf{th.rec, th.count, th.cap};
   }
-  static int attr_set = 0;
-  if (!attr_set) {
-    NNC_CHECK_CUDA(cudaFuncSetAttribute(k_apply_tc<0, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    NNC_CHECK_CUDA(cudaFuncSetAttribute(k_apply_tc<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    NNC_CHECK_CUDA(cudaFuncSetAttribute(k_apply_tc<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    NNC_CHECK_CUDA(cudaFuncSetAttribute(k_apply_tc<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = 1;
-  }
-  // Optional (NNCONV_L2_PERSIST=1): pin the Y ring in L2 with an access-policy window on the caller's stream
+  // Optional (l2_persist option): pin the Y ring in L2 with an access-policy window on the caller's stream
   // for the duration of this launch (persisting hits for the ring, everything else streaming).
   bool window_set = false;
-  if (const char* e = getenv("NNCONV_L2_PERSIST")) {
-    if (atoi(e) > 0) {
-      static int max_persist = -1;
-      if (max_persist < 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-        if (max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(max_persist));
-      }
-      const size_t ring_bytes = static_cast<size_t>(ring) * nb * NY * 2;
-      if (max_persist > 0) {
-        cudaStreamAttrValue v{};
-        v.accessPolicyWindow.base_ptr = Yring;
-        v.accessPolicyWindow.num_bytes = ring_bytes;
-        v.accessPolicyWindow.hitRatio = ring_bytes <= static_cast<size_t>(max_persist)
-                                            ? 1.0f
-                                            : static_cast<float>(max_persist) / static_cast<float>(ring_bytes);
-        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        window_set = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess;
-      }
+  if (opt.l2_persist > 0) {
+    static int max_persist = -1;
+    if (max_persist < 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      if (max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(max_persist));
+    }
+    const size_t ring_bytes = static_cast<size_t>(ring) * nb * NY * 2 * kmul;
+    if (max_persist > 0) {
+      cudaStreamAttrValue v{};
+      v.accessPolicyWindow.base_ptr = Yring;
+      v.accessPolicyWindow.num_bytes = ring_bytes;
+      v.accessPolicyWindow.hitRatio = ring_bytes <= static_cast<size_t>(max_persist)
+                                          ? 1.0f
+                                          : static_cast<float>(max_persist) / static_cast<float>(ring_bytes);
+      v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      window_set = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v) == cudaSuccess;
     }
   }
-  // every CTA must be resident (the flags couple all CTAs): exactly one CTA per SM, never more than #SMs
+  // exactly one CTA per SM, never more than #SMs (see launch_variant about co-residency)
   const int grid = tc_num_sms();
-  if (ybn == 64) {
-    if (bf) k_apply_tc<1, 64><<<grid, kThreads, as.smem_bytes, st>>>(tmH, tmY, tmX, tmW, a);
-    else k_apply_tc<0, 64><<<grid, kThreads, as.smem_bytes, st>>>(tmH, tmY, tmX, tmW, a);
-  } else {
-    if (bf) k_apply_tc<1, 128><<<grid, kThreads, as.smem_bytes, st>>>(tmH, tmY, tmX, tmW, a);
-    else k_apply_tc<0, 128><<<grid, kThreads, as.smem_bytes, st>>>(tmH, tmY, tmX, tmW, a);
-  }
+  const bool coop = opt.no_coop == 0;
+  if (ybn == 64) s = bf ? launch_variant<1, 64>(grid, as.smem_bytes, coop, st, tmH, tmY, tmX, tmW, a)
+                        : launch_variant<0, 64>(grid, as.smem_bytes, coop, st, tmH, tmY, tmX, tmW, a);
+  else s = bf ? launch_variant<1, 128>(grid, as.smem_bytes, coop, st, tmH, tmY, tmX, tmW, a)
+              : launch_variant<0, 128>(grid, as.smem_bytes, coop, st, tmH, tmY, tmX, tmW, a);
   if (window_set) {
     cudaStreamAttrValue v{};
     v.accessPolicyWindow.num_bytes = 0;
     cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &v);
   }
-  NNC_CHECK_LAUNCH();
-  return NNCONV_OK;
+  return s;
 }
 
 }  // namespace nnc

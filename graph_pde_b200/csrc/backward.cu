@@ -298,7 +298,7 @@ int backward_fp32(const Plan* P, const Weights* W, const float* edge_attr, const
     while (c0 < P->n_src) {
       int c1 = c0;
       size_t used = 0;
-      while (c1 < P->n_src) {
+      while (c1 < P->n_src && c1 - c0 < 65535) {    // the grouped GEMMs put the source index on grid.z (<= 65535)
         const size_t add = L.per_node + L.per_edge * static_cast<size_t>(hgp[c1 + 1] - hgp[c1]);
         if (used + add + 4096 > avail && c1 > c0) break;
         NNC_REQUIRE(used + add + 4096 <= avail, NNCONV_ERR_WORKSPACE, "backward: workspace too small for one source group");

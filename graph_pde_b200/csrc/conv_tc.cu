@@ -29,6 +29,7 @@
 #include <cstdlib>
 
 #include "kernels.h"
+#include "options.h"
 #include "tc05.cuh"
 #include "tmap.h"
 
@@ -306,7 +307,7 @@ bool conv_shape(int cout, int Kp, ConvShape* cs) {
   const int bar_bytes = 512;
   const int acc_cols = 2 * kTU * cout;
   if (acc_cols > 512) return false;
-  const bool one_per_sm = getenv("NNCONV_CONV_ONE_PER_SM") != nullptr;   // measurement knob
+  const bool one_per_sm = options().conv_one_per_sm != 0;   // measurement knob
   for (int two = one_per_sm ? 0 : 1; two >= 0; --two) {
     if (two && acc_cols > 256) continue;
     const int budget = two ? kSmemTwoPerSm : 227 * 1024;
@@ -332,7 +333,8 @@ bool conv_shape(int cout, int Kp, ConvShape* cs) {
 }  // namespace
 
 bool tc_shapes_supported(const Weights* W) {
-  if (W->prec != PREC_F16 && W->prec != PREC_BF16) return false;
+  if (W->prec != PREC_F16 && W->prec != PREC_BF16 && W->prec != PREC_F16X2) return false;
+  if (W->split) return apply_fused_supported(W);   // split precision exists in the fused kernel only
   ConvShape cs;
   return conv_shape(W->cout, W->Kp, &cs);
 }
@@ -363,9 +365,8 @@ int launch_conv_tc(int prec, const Plan* P, const void* h, int Kp, const void* Y
   a.inv_deg = aggr_mean ? P->inv_deg : nullptr; a.cvec = cvec; a.xs = xs; a.out = out;
   a.tile_begin = tile_begin; a.tile_end = tile_end; a.c0 = c0; a.cout = cout;
   a.nb_slots = cs.nb_slots; a.passes = cs.passes; a.a_stages = cs.a_stages;
-  if (const char* e = getenv("NNCONV_CONV_STAGES")) { int v = atoi(e); if (v >= 2 && v < a.a_stages) a.a_stages = v; }
-  a.debug = 0;
-  if (const char* e = getenv("NNCONV_DEBUG")) a.debug = atoi(e);
+  { const int v = options().conv_stages; if (v >= 2 && v < a.a_stages) a.a_stages = v; }
+  a.debug = options().conv_debug;
   static int attr_set[2] = {0, 0};
   if (!attr_set[bf]) {
     if (bf) NNC_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

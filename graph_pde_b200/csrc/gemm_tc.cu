@@ -10,6 +10,7 @@
 // ring of kStages; accumulators are double buffered in TMEM (2 x BLOCK_N columns) so the epilogue of
 // tile i overlaps the MMAs of tile i+1.
 #include "kernels.h"
+#include "options.h"
 #include "tc05.cuh"
 #include "tmap.h"
 
@@ -41,6 +42,13 @@ struct GemmTcArgs {
   // no block-level barrier, and the store of piece i drains while piece i+1 is converted.
   int tma_store;
   int bias_v4;         // bias is 16-byte aligned: float4 loads
+  // PREC_F16X2 (see plan.h): a_split_nk = K/3/64 > 0 -> A holds [hi | lo] (2K/3 columns) and K block kb reads
+  // A chunk (kb < nk ? kb : kb - nk), i.e. [hi | hi | lo] against B = [hi | lo | hi]; c_split -> the fp32 result is
+  // written as the pair hi = fp16(v) at column c and lo = fp16(v - hi) at column c + N (row-major, ldc = 2N) or at
+  // chunk (c / 64) + N / 64 (chunk-major).
+  int a_split_nk;
+  int c_split;
+  int* overflow;       // counts 32-column pieces holding a value beyond the fp16 range (fp16 outputs only), or nullptr
   TraceBuf trace;
   unsigned int trace_seq;
 };
@@ -124,7 +132,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         mbar_wait(&empty[stage], phase ^ 1u);
         if (elect_one()) {
           mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-          tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full[stage], kb * Cfg::kBlockK,
+          const int ka = (a.a_split_nk > 0 && kb >= a.a_split_nk) ? kb - a.a_split_nk : kb;
+          tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full[stage], ka * Cfg::kBlockK,
                       a.a_row0 + mb * Cfg::kBlockM, kEvictNormal);
           tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full[stage], kb * Cfg::kBlockK, nb * BLOCK_N,
                       kEvictLast);
@@ -197,7 +206,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int col0 = nb * BLOCK_N + half * (BLOCK_N / 2) + cc * 32;
         if (col0 < a.N && (row_ok || use_tma)) {
           const uint32_t* vv = v[cc & 1];
-          uint32_t packed[16];
+          uint32_t packed[16], packed_lo[16];
+          float vmax = 0.f;
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             float f[4] = {__uint_as_float(vv[4 * j4]), __uint_as_float(vv[4 * j4 + 1]),
@@ -215,46 +225,61 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
               for (int q = 0; q < 4; ++q) f[q] = fmaxf(f[q], 0.f);
             }
+            if (FMT == 0 && a.overflow != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) vmax = fmaxf(vmax, fabsf(f[q]));
+            }
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
               if (FMT == 0) {
                 __half2 h = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
                 packed[2 * j4 + q] = *reinterpret_cast<uint32_t*>(&h);
+                if (a.c_split) {
+                  const float2 hf = __half22float2(h);
+                  __half2 l = __floats2half2_rn(f[2 * q] - hf.x, f[2 * q + 1] - hf.y);
+                  packed_lo[2 * j4 + q] = *reinterpret_cast<uint32_t*>(&l);
+                }
               } else {
                 __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
                 packed[2 * j4 + q] = *reinterpret_cast<uint32_t*>(&h);
               }
             }
           }
-          if (use_tma) {
-            const uint32_t buf = stage0 + (piece & 1) * 2048;
-            const bool issuer = elect_one();                  // same lane every time: bulk groups are per thread
-            if (issuer) bulk_wait_read1();                    // the store issued two pieces ago has left this buffer
-            __syncwarp();
+          if (FMT == 0 && a.overflow != nullptr && row_ok && !(vmax <= 65504.f)) atomicAdd(a.overflow, 1);
+          // one [32 rows x 32 cols] piece at column colx of the (possibly doubled) output
+          auto store_piece = [&](const uint32_t* pk, int colx) {
+            if (use_tma) {
+              const uint32_t buf = stage0 + (piece & 1) * 2048;
+              const bool issuer = elect_one();                  // same lane every time: bulk groups are per thread
+              if (issuer) bulk_wait_read1();                    // the store issued two pieces ago has left this buffer
+              __syncwarp();
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              st_shared_v4(buf + lane * 64 + ((static_cast<uint32_t>(u) ^ sw) << 4), packed[4 * u], packed[4 * u + 1],
-                           packed[4 * u + 2], packed[4 * u + 3]);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (issuer) {
-              const int r0 = mb * Cfg::kBlockM + quarter * 32;
-              if (a.chunk_rows_pad > 0)
-                tma_store_2d(&tmC, buf, col0 & 63,
-                             static_cast<int>((col0 >> 6) * a.chunk_rows_pad + a.c_row0 + r0));
-              else
-                tma_store_2d(&tmC, buf, col0, r0);
-              bulk_commit();
+              for (int u = 0; u < 4; ++u)
+                st_shared_v4(buf + lane * 64 + ((static_cast<uint32_t>(u) ^ sw) << 4), pk[4 * u], pk[4 * u + 1],
+                             pk[4 * u + 2], pk[4 * u + 3]);
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (issuer) {
+                const int r0 = mb * Cfg::kBlockM + quarter * 32;
+                if (a.chunk_rows_pad > 0)
+                  tma_store_2d(&tmC, buf, colx & 63,
+                               static_cast<int>((colx >> 6) * a.chunk_rows_pad + a.c_row0 + r0));
+                else
+                  tma_store_2d(&tmC, buf, colx, r0);
+                bulk_commit();
+              }
+              ++piece;
+            } else if (row_ok) {
+              uint16_t* dst = a.chunk_rows_pad > 0
+                                  ? reinterpret_cast<uint16_t*>(a.C) +
+                                        (static_cast<int64_t>(colx >> 6) * a.chunk_rows_pad + grow) * 64 + (colx & 63)
+                                  : crow + colx;
+              st_global_v8(dst, pk);            // 2 x 32 B: full sectors (16 B stores were half-used
+              st_global_v8(dst + 16, pk + 8);   // sectors, ncu r1a)
             }
-            ++piece;
-          } else {
-            uint16_t* dst = a.chunk_rows_pad > 0
-                                ? reinterpret_cast<uint16_t*>(a.C) +
-                                      (static_cast<int64_t>(col0 >> 6) * a.chunk_rows_pad + grow) * 64 + (col0 & 63)
-                                : crow + col0;
-            st_global_v8(dst, packed);            // 2 x 32 B: full sectors (16 B stores were half-used
-            st_global_v8(dst + 16, packed + 8);   // sectors, ncu r1a)
-          }
+          };
+          store_piece(packed, col0);
+          if (FMT == 0 && a.c_split) store_piece(packed_lo, col0 + a.N);
         }
         if (cc + 1 < kChunks) tmem_ld_wait();
       }
@@ -323,11 +348,15 @@ int tc_num_sms() { return g_num_sms; }
 
 int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a_row0, int M, int K, const void* B,
                    int N, const float* bias, int relu, void* C, int64_t ldc, cudaStream_t st, const PipeFlags* pf,
-                   int64_t chunk_rows_pad, int64_t c_row0) {
+                   int64_t chunk_rows_pad, int64_t c_row0, int split_flags, int* overflow) {
   if (M <= 0 || N <= 0) return NNCONV_OK;
   int s = tc_init();
   if (s != NNCONV_OK) return s;
-  NNC_REQUIRE(prec == PREC_F16 || prec == PREC_BF16, NNCONV_ERR_ARG, "gemm_tc: 16-bit precisions only");
+  NNC_REQUIRE(prec == PREC_F16 || prec == PREC_BF16 || prec == PREC_F16X2, NNCONV_ERR_ARG, "gemm_tc: 16-bit precisions only");
+  const bool a_split = (split_flags & GEMM_A_SPLIT) != 0, c_split = (split_flags & GEMM_C_SPLIT) != 0;
+  NNC_REQUIRE(!a_split || K % 192 == 0, NNCONV_ERR_ARG, "gemm_tc: split A needs K = 3 x a multiple of 64");
+  NNC_REQUIRE(!(a_split || c_split) || prec != PREC_BF16, NNCONV_ERR_ARG, "gemm_tc: split operands are fp16 only");
+  const int nmul = c_split ? 2 : 1;
   NNC_REQUIRE(K % 64 == 0 && N % 64 == 0 && K >= 64, NNCONV_ERR_ARG, "gemm_tc: K=%d N=%d must be multiples of 64", K, N);
   NNC_REQUIRE(ldc % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 31) == 0, NNCONV_ERR_ARG,
               "gemm_tc: C must be 32-byte aligned with ldc a multiple of 16 elements");
@@ -335,7 +364,8 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
   const bool small = pf && pf->small_footprint && N >= 128;
   const int BN = small ? 128 : (N % 256 == 0 || N > 256) ? 256 : (N % 128 == 0 || N > 128) ? 128 : 64;
   CUtensorMap tmA, tmB;
-  s = make_tmap_2d_16b(&tmA, bf, A_base, static_cast<uint64_t>(a_rows_total), static_cast<uint64_t>(K), 128);
+  s = make_tmap_2d_16b(&tmA, bf, A_base, static_cast<uint64_t>(a_rows_total),
+                       static_cast<uint64_t>(a_split ? K / 3 * 2 : K), 128);
   if (s != NNCONV_OK) return s;
   s = make_tmap_2d_16b(&tmB, bf, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), BN);
   if (s != NNCONV_OK) return s;
@@ -343,6 +373,9 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
   a.M = M; a.N = N; a.K = K; a.a_row0 = static_cast<int>(a_row0); a.bias = bias; a.relu = relu; a.C = C; a.ldc = ldc;
   a.chunk_rows_pad = chunk_rows_pad;
   a.c_row0 = c_row0;
+  a.a_split_nk = a_split ? K / 192 : 0;
+  a.c_split = c_split ? 1 : 0;
+  a.overflow = (overflow != nullptr && !bf) ? overflow : nullptr;
   {
     TraceHandle th = trace_get();
     static unsigned int launch_seq = 0;
@@ -351,19 +384,19 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
   }
   // TMA-store epilogue: [32 x 32] pieces; rows past M are clipped by the tensor bounds (row-major) or land in
   // the row padding of each chunk panel (chunk-major, chunk_rows_pad >= round_up(c_row0 + M, 32))
-  static const bool no_tma_store = getenv("NNCONV_GEMM_DIRECT_STORE") != nullptr;
+  const bool no_tma_store = options().gemm_direct_store != 0;
   a.tma_store = 0;
   a.bias_v4 = bias != nullptr && (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
   CUtensorMap tmC = tmA;
   const bool panel_ok = chunk_rows_pad > 0
                             ? ((c_row0 + M + 31) / 32 * 32 <= chunk_rows_pad &&
-                               static_cast<int64_t>(N / 64) * chunk_rows_pad < (int64_t(1) << 31))
-                            : ldc == N;
+                               static_cast<int64_t>(nmul * N / 64) * chunk_rows_pad < (int64_t(1) << 31))
+                            : ldc == static_cast<int64_t>(nmul) * N;
   if (!no_tma_store && pf == nullptr && panel_ok) {
     if (chunk_rows_pad > 0) {
-      s = make_tmap_store_16b(&tmC, bf, C, static_cast<uint64_t>(N / 64) * static_cast<uint64_t>(chunk_rows_pad), 64);
+      s = make_tmap_store_16b(&tmC, bf, C, static_cast<uint64_t>(nmul * N / 64) * static_cast<uint64_t>(chunk_rows_pad), 64);
     } else {
-      s = make_tmap_store_16b(&tmC, bf, C, static_cast<uint64_t>(M), static_cast<uint64_t>(N));
+      s = make_tmap_store_16b(&tmC, bf, C, static_cast<uint64_t>(M), static_cast<uint64_t>(nmul) * N);
     }
     if (s != NNCONV_OK) return s;
     a.tma_store = 1;

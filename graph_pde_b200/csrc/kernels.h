@@ -46,27 +46,22 @@ struct PipeFlags {
 
 // ---- gemm_tc.cu (tcgen05): C[M, N] (16-bit) = act(A[M, K] * B[N, K]^T + bias); A rows start at a_row0 of the
 // tensor A_base[a_rows_total, K]; K, N multiples of 64.  bias == nullptr -> no bias, relu flag separate.
+// split_flags (PREC_F16X2): GEMM_A_SPLIT -> A is [hi | lo] with 2K/3 columns and B is [hi | lo | hi] with K columns;
+// GEMM_C_SPLIT -> C receives [hi | lo] pairs (2N columns / 2N/64 chunks).  overflow: device counter of output
+// pieces that left the fp16 range (nullable).
+enum { GEMM_A_SPLIT = 1, GEMM_C_SPLIT = 2 };
 int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a_row0, int M, int K,
                    const void* B, int N, const float* bias, int relu, void* C, int64_t ldc, cudaStream_t st,
-                   const PipeFlags* pf = nullptr, int64_t chunk_rows_pad = 0, int64_t c_row0 = 0);
+                   const PipeFlags* pf = nullptr, int64_t chunk_rows_pad = 0, int64_t c_row0 = 0,
+                   int split_flags = 0, int* overflow = nullptr);
 
 // ---- conv_tc.cu (tcgen05): per-source contraction + scatter for tiles [tile_begin, tile_end)
 int launch_conv_tc(int prec, const Plan* P, const void* h, int Kp, const void* Y, int64_t y_nodes, int cout,
                    int tile_begin, int tile_end, int c0, const float* cvec, const float* xs, int aggr_mean, float* out,
                    cudaStream_t st, const PipeFlags* pf = nullptr);
 
-// ---- mlp_fused_tc.cu: first two MLP layers in one kernel (h1 never leaves the SM)
-int launch_mlp12_tc(int prec, const void* A1, int64_t rows, int k_in, const void* W1aug, int K1p, const void* W2,
-                    int N, const float* bias2, void* C, int64_t ldc, int64_t chunk_rows_pad, int64_t c_row0,
-                    cudaStream_t st);
-
-// ---- mlp_ring_tc.cu: first two MLP layers as two pipelines per CTA meeting in an L2-resident ring
-size_t mlp_ring_bytes(int K1p);
-int launch_mlp_ring_tc(int prec, const void* A1, int64_t rows, int k_in, const void* W1aug, int K1p, const void* W2,
-                       int N, const float* bias2, void* ring, void* C, int64_t ldc, int64_t chunk_rows_pad,
-                       int64_t c_row0, cudaStream_t st);
-
 // ---- apply_tc.cu: ONE persistent kernel per application (Y GEMM + contraction pipelines in every CTA)
+constexpr int kApplyCannotCoSchedule = 1000;   // private status of launch_apply_tc: cooperative launch impossible
 bool apply_fused_supported(const Weights* W);
 int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, const void* Xc, void* Yring, int nb,
                     int ring, const float* cvec, const float* xs, int aggr_mean, float* out, int* flags,

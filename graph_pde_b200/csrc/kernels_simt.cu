@@ -47,6 +47,35 @@ __global__ void k_w3p(const float* __restrict__ WL, int cin, int cout, int K, in
   dst[idx] = cvt<T>(v);
 }
 
+// ---- PREC_F16X2 weight images: K is tripled, [hi(W) | lo(W) | hi(W)], to pair with activations read as
+// [hi(a) | hi(a) | lo(a)]:  a.W ~= hi*hi + hi*lo + lo*hi  (the dropped lo*lo term is 2^-22 relative)
+__device__ __forceinline__ __half split_part(float v, int part) {
+  const __half hi = __float2half_rn(v);
+  return part == 1 ? __float2half_rn(v - __half2float(hi)) : hi;
+}
+__global__ void k_pad_convert_split3(const float* __restrict__ src, int R, int C, __half* __restrict__ dst, int Rp,
+                                     int Cp) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<int64_t>(Rp) * 3 * Cp) return;
+  const int r = static_cast<int>(i / (3 * Cp)), cc = static_cast<int>(i % (3 * Cp));
+  const int part = cc / Cp, c = cc % Cp;
+  const float v = (r < R && c < C) ? src[static_cast<int64_t>(r) * C + c] : 0.f;
+  dst[i] = split_part(v, part);
+}
+__global__ void k_w3p_split3(const float* __restrict__ WL, int cin, int cout, int K, int Kp, int cin_p,
+                             __half* __restrict__ dst) {
+  int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(cout) * Kp * 3 * cin_p;
+  if (idx >= total) return;
+  const int ii = static_cast<int>(idx % (3 * cin_p));
+  const int part = ii / cin_p, i = ii % cin_p;
+  const int64_t ok = idx / (3 * cin_p);
+  const int k = static_cast<int>(ok % Kp);
+  const int o = static_cast<int>(ok / Kp);
+  const float v = (i < cin && k < K) ? WL[(static_cast<int64_t>(i) * cout + o) * K + k] : 0.f;
+  dst[idx] = split_part(v, part);
+}
+
 // First layer: h1[p, j] = relu(b1[j] + sum_c W1[j, c] * edge_attr[perm[p], c]),  j < kp1 (pad rows of W1/b1 are 0)
 // identity (single-Linear MLP): h[p, j] = edge_attr[perm[p], j] (zero padded), no ReLU.
 constexpr int kL1Edges = 32;
@@ -106,6 +135,8 @@ k_edge_layer1(const float* __restrict__ edge_attr, const int* __restrict__ perm,
 // fp32-grade accuracy although it runs as a 16-bit tcgen05 GEMM (utilities.py:223-227, first layer).
 template <typename T>
 __device__ __forceinline__ float as_float(T v);
+template <>
+__device__ __forceinline__ float as_float<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float as_float<__half>(__half v) { return __half2float(v); }
 template <>
@@ -183,7 +214,8 @@ __global__ void k_out_init(const float* __restrict__ x, const float* __restrict_
 // linear in x, so the operand row is normalised to (0.5, 1] -- exactly, the scale only touches the exponent --
 // and the epilogue multiplies the accumulator by xs[c].  Without it node features beyond the fp16 range
 // (65504; an untrained MGKN V-cycle reaches 5e5 after 4 depth iterations) turned into inf/NaN.
-template <typename T>
+// SPLIT (PREC_F16X2): Xc row = [hi | hi | lo] of the normalised row (3 * cin_p columns).
+template <typename T, int SPLIT = 0>
 __global__ void k_src_prep(const float* __restrict__ x, const int* __restrict__ src_nodes, int S, int cin, int cin_p,
                            int cout, const float* __restrict__ B3, T* __restrict__ Xc, float* __restrict__ cvec,
                            float* __restrict__ xs) {
@@ -211,8 +243,19 @@ __global__ void k_src_prep(const float* __restrict__ x, const int* __restrict__ 
     inv = 1.f / sc;                                // exact (power of two)
     if (threadIdx.x == 0) xs[c] = sc;
   }
-  for (int i = threadIdx.x; i < cin_p; i += blockDim.x)
-    Xc[static_cast<int64_t>(c) * cin_p + i] = cvt<T>(i < cin ? myx[i] * inv : 0.f);
+  if (SPLIT) {
+    for (int i = threadIdx.x; i < cin_p; i += blockDim.x) {
+      const float v = i < cin ? myx[i] * inv : 0.f;
+      const T hi = cvt<T>(v);
+      T* row = Xc + static_cast<int64_t>(c) * 3 * cin_p;
+      row[i] = hi;
+      row[cin_p + i] = hi;
+      row[2 * cin_p + i] = cvt<T>(v - as_float<T>(hi));
+    }
+  } else {
+    for (int i = threadIdx.x; i < cin_p; i += blockDim.x)
+      Xc[static_cast<int64_t>(c) * cin_p + i] = cvt<T>(i < cin ? myx[i] * inv : 0.f);
+  }
   for (int o = threadIdx.x; o < cout; o += blockDim.x) {
     float acc = 0.f;
     for (int i = 0; i < cin; ++i) acc = fmaf(myx[i], B3[i * cout + o], acc);
@@ -328,6 +371,13 @@ int launch_pad_convert_t(const float* src, int R, int C, void* dst, int Rp, int 
 }  // namespace
 
 int launch_pad_convert(int prec, const float* src, int R, int C, void* dst, int Rp, int Cp, cudaStream_t st) {
+  if (prec == PREC_F16X2) {
+    const int64_t total = static_cast<int64_t>(Rp) * 3 * Cp;
+    if (total == 0) return NNCONV_OK;
+    k_pad_convert_split3<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(src, R, C, static_cast<__half*>(dst), Rp, Cp);
+    NNC_CHECK_LAUNCH();
+    return NNCONV_OK;
+  }
   if (prec == PREC_FP32) return launch_pad_convert_t<float>(src, R, C, dst, Rp, Cp, st);
   if (prec == PREC_F16) return launch_pad_convert_t<__half>(src, R, C, dst, Rp, Cp, st);
   return launch_pad_convert_t<__nv_bfloat16>(src, R, C, dst, Rp, Cp, st);
@@ -335,6 +385,11 @@ int launch_pad_convert(int prec, const float* src, int R, int C, void* dst, int 
 
 int launch_w3p(int prec, const float* WL, int cin, int cout, int K, int Kp, int cin_p, void* dst, cudaStream_t st) {
   int64_t total = static_cast<int64_t>(cout) * Kp * cin_p;
+  if (prec == PREC_F16X2) {
+    k_w3p_split3<<<(unsigned)ceil_div64(3 * total, 256), 256, 0, st>>>(WL, cin, cout, K, Kp, cin_p, static_cast<__half*>(dst));
+    NNC_CHECK_LAUNCH();
+    return NNCONV_OK;
+  }
   unsigned g = (unsigned)ceil_div64(total, 256);
   if (prec == PREC_FP32) k_w3p<float><<<g, 256, 0, st>>>(WL, cin, cout, K, Kp, cin_p, static_cast<float*>(dst));
   else if (prec == PREC_F16) k_w3p<__half><<<g, 256, 0, st>>>(WL, cin, cout, K, Kp, cin_p, static_cast<__half*>(dst));
@@ -352,7 +407,7 @@ int launch_edge_layer1(int prec, const float* edge_attr, const int* perm, int64_
   if (prec == PREC_FP32)
     k_edge_layer1<float><<<g, 256, sm, st>>>(edge_attr, perm, e_begin, e_count, k_in, W1, b1, kp1, identity,
                                              static_cast<float*>(out), chunk_rows_pad, out_row0);
-  else if (prec == PREC_F16)
+  else if (prec == PREC_F16 || prec == PREC_F16X2)
     k_edge_layer1<__half><<<g, 256, sm, st>>>(edge_attr, perm, e_begin, e_count, k_in, W1, b1, kp1, identity,
                                               static_cast<__half*>(out), chunk_rows_pad, out_row0);
   else
@@ -366,7 +421,7 @@ int launch_build_a1(int prec, const float* edge_attr, const int* perm, int64_t e
                     void* A1, cudaStream_t st) {
   if (e_count <= 0) return NNCONV_OK;
   unsigned g = (unsigned)ceil_div64(e_count * 8, 256);
-  if (prec == PREC_F16)
+  if (prec == PREC_F16 || prec == PREC_F16X2)
     k_build_a1<__half><<<g, 256, 0, st>>>(edge_attr, perm, e_begin, e_count, k_in, static_cast<__half*>(A1));
   else
     k_build_a1<__nv_bfloat16><<<g, 256, 0, st>>>(edge_attr, perm, e_begin, e_count, k_in,
@@ -377,7 +432,7 @@ int launch_build_a1(int prec, const float* edge_attr, const int* perm, int64_t e
 
 int launch_w1aug(int prec, const float* W1, const float* b1, int k1, int kp1, int k_in, void* dst, cudaStream_t st) {
   unsigned g = (unsigned)ceil_div(kp1 * 64, 256);
-  if (prec == PREC_F16) k_w1aug<__half><<<g, 256, 0, st>>>(W1, b1, k1, kp1, k_in, static_cast<__half*>(dst));
+  if (prec == PREC_F16 || prec == PREC_F16X2) k_w1aug<__half><<<g, 256, 0, st>>>(W1, b1, k1, kp1, k_in, static_cast<__half*>(dst));
   else k_w1aug<__nv_bfloat16><<<g, 256, 0, st>>>(W1, b1, k1, kp1, k_in, static_cast<__nv_bfloat16*>(dst));
   NNC_CHECK_LAUNCH();
   return NNCONV_OK;
@@ -402,6 +457,8 @@ int launch_src_prep(int prec, const float* x, const int* src_nodes, int S, int c
     k_src_prep<float><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3, static_cast<float*>(Xc), cvec, nullptr);
   else if (prec == PREC_F16)
     k_src_prep<__half><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3, static_cast<__half*>(Xc), cvec, xs);
+  else if (prec == PREC_F16X2)
+    k_src_prep<__half, 1><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3, static_cast<__half*>(Xc), cvec, xs);
   else
     k_src_prep<__nv_bfloat16><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3,
                                                 static_cast<__nv_bfloat16*>(Xc), cvec, xs);

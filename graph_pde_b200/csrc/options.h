@@ -1,0 +1,29 @@
+// Tuning / debugging knobs of libnnconv_b200.  They are read from the environment ONCE (first nnconv_init)
+// and can afterwards be changed through nnconv_set_option(); nothing on the per-application path calls getenv.
+#pragma once
+
+namespace nnc {
+
+struct Options {
+  int no_fuse;            // NNCONV_NO_FUSE: per-batch Y GEMM + contraction kernels instead of the persistent fused kernel
+  int no_pipe;            // NNCONV_NO_PIPE: plain stream order for the per-batch kernels (no PDL / flags)
+  int ring;               // NNCONV_RING: Y ring depth of the fused kernel (2..8, default 3)
+  int y_block_n;          // NNCONV_Y_BLOCKN: N tile of the Y pipeline (64 default | 128)
+  int apply_stages;       // NNCONV_APPLY_STAGES: cap on the A stages of the fused kernel (0 = no cap)
+  int debug_scatter;      // NNCONV_DEBUG_SCATTER: timing experiments only (wrong results)
+  int y_store_policy;     // NNCONV_Y_STORE_POLICY: 0 normal, 1 evict-last, 2 evict-first
+  int l2_persist;         // NNCONV_L2_PERSIST: access-policy window over the Y ring
+  int conv_one_per_sm;    // NNCONV_CONV_ONE_PER_SM
+  int conv_stages;        // NNCONV_CONV_STAGES
+  int conv_debug;         // NNCONV_DEBUG
+  int gemm_direct_store;  // NNCONV_GEMM_DIRECT_STORE: st.global epilogue instead of TMA stores
+  int trace;              // NNCONV_TRACE: CTA timeline records
+  int no_coop;            // NNCONV_NO_COOP: launch the fused kernel without the cooperative attribute
+  int overflow_check;     // NNCONV_OVERFLOW_CHECK: count non-finite / saturated 16-bit edge features (default 1)
+};
+
+Options& options();                          // initialised from the environment on first use
+int option_set(const char* name, int value); // 0 ok, -1 unknown name
+int option_get(const char* name, int* value);
+
+}  // namespace nnc

@@ -8,7 +8,12 @@ namespace nnc {
 
 constexpr int kMaxLayers = 8;
 
-enum Precision : int { PREC_FP32 = 0, PREC_F16 = 1, PREC_BF16 = 2 };
+enum Precision : int { PREC_FP32 = 0, PREC_F16 = 1, PREC_BF16 = 2, PREC_F16X2 = 3 };
+// PREC_F16X2: every tensor-core operand is carried as an fp16 pair (hi, lo) with hi = fp16(v), lo = fp16(v - hi)
+// (~22 mantissa bits) and every product as hi*hi + hi*lo + lo*hi in the fp32 accumulator: fp32-grade results on
+// the fp16 tensor pipe at 3x the MMA work and 2x the activation bytes.
+inline bool prec_is_bf16(int prec) { return prec == PREC_BF16; }
+inline bool prec_is_split(int prec) { return prec == PREC_F16X2; }
 
 struct Plan {
   int64_t E, N;
@@ -46,13 +51,14 @@ struct Weights {
   int cin, cout, cin_p;
   int K, Kp;                    // width of the hoisted per-edge feature h_last (= dims[L-1]) and its padding
   int prec;
+  int split;                    // PREC_F16X2: activations are [hi | lo] pairs (2 x width), weights [hi | lo | hi] (3 x K)
   size_t esize;                 // bytes per element of activations / tensor-core operands
   const float* W1;              // [kp[1], k_in] fp32 (zero padded rows); nullptr when n_layers == 1
   const float* b1;              // [kp[1]]
   const void* W1aug;            // [kp[1], 64] in `prec`: split hi/lo first layer incl. bias (tensor-core path), or nullptr
-  const void* Wh[kMaxLayers];   // hidden layers l = 2 .. L-1: [kp[l], kp[l-1]] in `prec`
+  const void* Wh[kMaxLayers];   // hidden layers l = 2 .. L-1: [kp[l], kp[l-1]] in `prec` (split: [kp[l], 3*kp[l-1]])
   const float* bh[kMaxLayers];  // [kp[l]] fp32
-  const void* W3p;              // [cout*Kp, cin_p] in `prec`:  W3p[(o*Kp + k), i] = W_L[i*cout + o, k]
+  const void* W3p;              // [cout*Kp, cin_p] in `prec`:  W3p[(o*Kp + k), i] = W_L[i*cout + o, k] (split: 3*cin_p columns)
   const float* B3;              // [cin, cout] fp32 = b_L viewed (in, out)
 };
 

@@ -4,6 +4,7 @@
 #include <cstdlib>
 
 #include "kernels.h"
+#include "options.h"
 #include <mutex>
 
 namespace nnc {
@@ -103,8 +104,7 @@ bool g_trace_checked = false;
 TraceHandle trace_get() {
   if (!g_trace_checked) {
     g_trace_checked = true;
-    const char* e = getenv("NNCONV_TRACE");
-    if (e && atoi(e) > 0) {
+    if (options().trace > 0) {
       const unsigned int cap = 1u << 20;
       if (cudaMalloc(&g_trace.rec, static_cast<size_t>(cap) * 6 * sizeof(unsigned long long)) == cudaSuccess &&
           cudaMalloc(&g_trace.count, sizeof(unsigned int)) == cudaSuccess) {

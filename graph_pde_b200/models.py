@@ -84,13 +84,15 @@ class _VCycleBase(torch.nn.Module):
     def _ranges(self, data):
         # one device->host copy for ALL slice bounds (the reference indexes with 0-d CUDA tensors: one
         # implicit sync per bound, ~40 per depth iteration -- SURVEY 3.3)
-        key = (data.edge_index_range.data_ptr(), data.edge_index_down_range.data_ptr(),
-               data.edge_index_up_range.data_ptr())
-        if getattr(self, '_range_key', None) != key:
-            self._range_cache = (data.edge_index_down_range.tolist(), data.edge_index_range.tolist(),
-                                 data.edge_index_up_range.tolist())
-            self._range_key = key
-        return self._range_cache
+        # The cache entry HOLDS the three range tensors (so their storage cannot be freed and recycled for the
+        # next sample's ranges) and is valid only for the same tensor objects at the same version.
+        ts = (data.edge_index_down_range, data.edge_index_range, data.edge_index_up_range)
+        hit = getattr(self, '_range_cache', None)
+        if hit is None or any(a is not b for a, b in zip(hit[0], ts)) or hit[1] != tuple(t._version for t in ts):
+            vals = tuple(t.tolist() for t in ts)
+            hit = (ts, tuple(t._version for t in ts), vals)
+            self._range_cache = hit
+        return hit[2]
 
 
 class KernelInduced(_VCycleBase):
@@ -144,12 +146,12 @@ class MKGN(_VCycleBase):
     def _mid_edges(self, data, l, a, b):
         """edge_index_mid[:, a:b] - points[l] (:85) computed once per graph instead of once per call."""
         ei = data.edge_index_mid
-        key = (ei.data_ptr(), ei._version, l, a, b)
         hit = self._rebased.get(l)
-        if hit is None or hit[0] != key:
-            hit = (key, (ei[:, a:b] - self.points[l]).contiguous())
+        # the entry holds `ei` itself: same object + same version + same slice, or it is rebuilt
+        if hit is None or hit[0] is not ei or hit[1] != (ei._version, a, b):
+            hit = (ei, (ei._version, a, b), (ei[:, a:b] - self.points[l]).contiguous())
             self._rebased[l] = hit
-        return hit[1]
+        return hit[2]
 
     def forward(self, data):
         r_down, r_mid, r_up = self._ranges(data)

@@ -36,7 +36,9 @@ __all__ = ['NNConv_old', 'NNConv', 'ECConv', 'stats', 'clear_caches', 'default_p
 stats = {'launches': 0, 'plans_built': 0, 'edge_feature_passes': 0, 'applies': 0, 'weight_preps': 0}
 
 _PLAN_CACHE = collections.OrderedDict()
-_PLAN_CACHE_MAX = int(os.environ.get('NNCONV_B200_PLAN_CACHE', '64'))
+_PLAN_CACHE_MAX = int(os.environ.get('NNCONV_B200_PLAN_CACHE', '64'))                 # entries
+_PLAN_CACHE_MAX_BYTES = int(os.environ.get('NNCONV_B200_PLAN_CACHE_BYTES', str(2 << 30)))   # plan buffers + pinned edge_index
+_OVERFLOW_CHECK = os.environ.get('NNCONV_B200_OVERFLOW_CHECK', '1') != '0'
 _Y_BYTES = int(os.environ.get('NNCONV_B200_Y_BYTES', str(48 << 20)))       # Y ring: 3 x 128 sources at out=64, Kp=1024
 _EF_WS_BYTES = int(os.environ.get('NNCONV_B200_EF_WS_BYTES', str(4 << 30)))  # hidden-layer ping-pong chunk (4 GiB: 25 instead of 97 chunks at 241^2, -1 ms/step, run39)
 _BWD_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_WS_BYTES', str(2 << 30)))  # backward: activations per batch
@@ -88,6 +90,7 @@ class _Plan(object):
                                         ws_b.value, _ptr(tmp), tmp_b.value, _stream_ptr(dev), ctypes.byref(h)))
         self.handle = h
         self.key = _plan_key(edge_index, n_nodes, flow)
+        self.nbytes = self.ws.numel() + edge_index.numel() * edge_index.element_size()
         info = (ctypes.c_int64 * 8)()
         _lib.check(L.nnconv_plan_info(h, info, 8))
         self.E, self.N, self.n_src, self.n_tiles, self.max_out_deg, self.src_sorted = [int(v) for v in info[:6]]
@@ -108,7 +111,9 @@ def get_plan(edge_index, n_nodes, flow='source_to_target'):
         return plan
     plan = _Plan(edge_index, n_nodes, flow)
     _PLAN_CACHE[key] = plan
-    while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
+    # bounded by entries AND bytes (a 241^2 plan pins ~0.6 GB incl. the caller's edge_index); the newest plan stays
+    while len(_PLAN_CACHE) > 1 and (len(_PLAN_CACHE) > _PLAN_CACHE_MAX or
+                                    sum(p.nbytes for p in _PLAN_CACHE.values()) > _PLAN_CACHE_MAX_BYTES):
         _PLAN_CACHE.popitem(last=False)
     return plan
 
@@ -199,8 +204,14 @@ class NNConv_old(torch.nn.Module):
     (reference docstring: graph-neural-operator/nn_conv.py:198-232).
 
     Args are the reference's (nn_conv.py:234-241).  Extra keyword ``precision`` in
-    {'f16' (default), 'bf16', 'fp32'} selects the tensor-core operand type ('fp32' = CUDA-core path for
-    arbitrary shapes); ``flow`` is PyG's MessagePassing kwarg.
+    {'f16' (default), 'bf16', 'f16x2', 'fp32'} selects the tensor-core operand type: 'f16x2' carries every
+    operand as an fp16 (hi, lo) pair -- fp32-grade results (tolerance 2e-5) on the tensor cores at ~2.4x the
+    time of 'f16'; 'fp32' = CUDA-core path for arbitrary shapes.  ``flow`` is PyG's MessagePassing kwarg.
+
+    Caches: the down-converted weights and the x-independent edge features are cached per (parameter versions,
+    edge_attr version).  Optimizer steps, ``load_state_dict`` and ``train()/eval()`` invalidate them; writes that
+    bypass autograd's version counter (``p.data.copy_()``, ``p.data.clamp_()``) do NOT -- call ``invalidate()``
+    after such writes.
     """
 
     def __init__(self, in_channels, out_channels, nn, aggr='add', root_weight=True, bias=True, **kwargs):
@@ -262,6 +273,24 @@ class NNConv_old(torch.nn.Module):
     def __repr__(self):
         return '{}({}, {})'.format(self.__class__.__name__, self.in_channels, self.out_channels)
 
+    # -- cache control ----------------------------------------------------------------------------------
+    def invalidate(self):
+        """Drop the prepared-weight snapshots and cached edge features (needed after parameter writes that do
+        not bump the tensors' version counters, e.g. through ``.data``)."""
+        self._prepared = None
+        self._prepared_key = None
+        self._prepared32_key = None
+        self._prepared32 = None
+        self._h_cache.clear()
+
+    def train(self, mode=True):
+        self.invalidate()
+        return super(NNConv_old, self).train(mode)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.invalidate()
+        return super(NNConv_old, self)._load_from_state_dict(*args, **kwargs)
+
     # -- host-side sequencing ---------------------------------------------------------------------------
     def _get_prepared(self, precision):
         linears = _linear_chain(self.nn)
@@ -292,6 +321,15 @@ class NNConv_old(torch.nn.Module):
                                           ws_b.value, _stream_ptr(dev), ctypes.byref(n_l)))
         stats['launches'] += n_l.value
         stats['edge_feature_passes'] += 1
+        if _OVERFLOW_CHECK and prepared.precision in ('f16', 'fp16', 'f16x2') and \
+                not torch.cuda.is_current_stream_capturing():
+            cnt = ctypes.c_int64(0)
+            _lib.check(L.nnconv_edge_features_overflow(_ptr(ws), _stream_ptr(dev), ctypes.byref(cnt)))
+            if cnt.value:
+                raise FloatingPointError(
+                    'graph_pde_b200.NNConv: %d blocks of edge-MLP activations left the fp16 range (|h| > 65504 or '
+                    "NaN); use precision='bf16' or 'fp32' for this parameter scale (NNCONV_B200_OVERFLOW_CHECK=0 "
+                    'disables this check and its one host sync per edge-feature pass)' % cnt.value)
         self._h_cache[key] = (h, edge_attr)          # hold edge_attr so its address cannot be recycled
         return h
 

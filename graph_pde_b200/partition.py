@@ -31,15 +31,23 @@ def shard_indices(n_items, rank, world):
 def allreduce_gradients(module, group=None):
     """Sum-reduce parameter gradients across ranks (the reference's losses are sums over the batch,
     UAI1_full_resolution.py:265, so no rescale).  One flat all-reduce: ~21 MB for KernelNN(w=64, kw=1024)."""
-    grads = [p.grad for p in module.parameters() if p.grad is not None]
-    if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
-    flat = torch.cat([g.reshape(-1) for g in grads])
+    # EVERY rank reduces the same flat buffer: all trainable parameters in module order, zeros standing in for a
+    # missing .grad (a rank with an empty shard or an unused parameter must not shorten the buffer)
+    params = [p for p in module.parameters() if p.requires_grad]
+    if not params:
+        return
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     off = 0
-    for g in grads:
-        n = g.numel()
-        g.copy_(flat[off:off + n].view_as(g))
+    for p in params:
+        n = p.numel()
+        g = flat[off:off + n].view_as(p).to(p.dtype)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
         off += n
 
 

@@ -53,6 +53,9 @@ extern "C" {
 #define NNCONV_PREC_FP32 0 /* CUDA-core fp32 everywhere, any shape */
 #define NNCONV_PREC_F16 1  /* tcgen05 kind::f16, fp16 operands (10-bit mantissa, TF32-grade) */
 #define NNCONV_PREC_BF16 2 /* tcgen05 kind::f16, bf16 operands */
+/* fp32-grade results on the fp16 tensor pipe: every operand is an fp16 pair (hi, lo = fp16(v - hi)), every
+ * product hi*hi + hi*lo + lo*hi in the fp32 accumulator (3x the MMA work, 2x the activation bytes) */
+#define NNCONV_PREC_F16X2 3
 
 #define NNCONV_AGGR_ADD 0
 #define NNCONV_AGGR_MEAN 1
@@ -65,8 +68,14 @@ typedef struct nnconv_weights nnconv_weights_t; /* per parameter version: padded
 
 const char* nnconv_last_error(void);
 int nnconv_abi_version(void);
-/* checks the device (sm_100 class) and resolves the TMA descriptor encoder; idempotent */
+/* checks the device (sm_100 class), resolves the TMA descriptor encoder and reads the NNCONV_* tuning
+ * variables from the environment (once); idempotent */
 int nnconv_init(void);
+/* tuning / debugging knobs (csrc/options.h lists them: "no_fuse", "ring", "no_coop", ...).  The environment is
+ * consulted only by the first nnconv_init; afterwards knobs change through nnconv_set_option.  A value below
+ * -1000000 restores the built-in default. */
+int nnconv_set_option(const char* name, int value);
+int nnconv_get_option(const char* name, int* value);
 
 /* ---- plan: replaces the implicit structure PyG derives from edge_index inside propagate() -------- */
 int nnconv_plan_sizes(int64_t E, int64_t N, size_t* ws_bytes, size_t* tmp_bytes);
@@ -100,6 +109,11 @@ int nnconv_edge_features_sizes(const nnconv_plan_t* plan, const nnconv_weights_t
 int nnconv_edge_features(const nnconv_plan_t* plan, const nnconv_weights_t* w, const float* edge_attr /*[E,k_in]*/,
                          void* h, void* ws, size_t ws_bytes, void* stream, int64_t* launches /*nullable*/);
 
+/* Number of 32-column output pieces of the LAST nnconv_edge_features call on `ws` that left the fp16 range
+ * (|v| > 65504 or NaN; fp16 precisions only, always 0 for bf16 / fp32 or with option overflow_check = 0).
+ * Copies one int to the host and synchronises `stream`.  A non-zero count means h holds inf: use bf16 / fp32. */
+int nnconv_edge_features_overflow(const void* ws, void* stream, int64_t* count);
+
 /* ---- one NNConv application: gather + last Linear + per-edge contraction + scatter + root + bias --- */
 int nnconv_apply_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t want_y_bytes, size_t* ws_bytes);
 /* x [N,in] fp32, root [in,out] or NULL, bias [out] or NULL, out [N,out] fp32 (fully overwritten). */
@@ -131,6 +145,10 @@ int nnconv_profile_end(double* ms_by_kind, int64_t* launches_by_kind, int n_kind
  * {tag, blockIdx, smid, t_start, t_ready, t_end} (globaltimer ns); this copies the records to the host and
  * clears the buffer.  tag: 100 = K=64 GEMM, 101 = hidden GEMM, 200 = contraction. */
 int nnconv_debug_trace_dump(unsigned long long* host_rec, unsigned int max_rec, unsigned int* n_out);
+
+/* ---- test hook: occupy `n_ctas` CTA slots (each holding `smem_bytes` of shared memory) for `ns` nanoseconds on
+ * `stream` -- used to check that the persistent application kernel tolerates concurrently resident kernels. */
+int nnconv_debug_occupy(int n_ctas, int smem_bytes, long long ns, void* stream);
 
 /* ---- unit-test hook for the tcgen05 GEMM used by the hidden layers and the per-source matrices:
  * C[M,N] (16-bit) = act(A[M,K] * B[N,K]^T + bias); K, N multiples of 64; bias nullable. ------------- */
