@@ -388,7 +388,6 @@ def main():
     # ---- parity at the benchmarked configuration and precision + the fp32-grade (f16x2) line, rank 0 only
     parity, fp32_grade = None, None
     if rank == 0 and not args.no_parity:
-        import copy
         with torch.no_grad():
             x0 = model.fc1(dev_x[0])
             got = model.conv_stack(x0, ei, dev_ea[0])
@@ -402,9 +401,8 @@ def main():
                              'node features' % (args.workload, E, T))
         del got
         if args.precision == 'f16':
-            m2 = copy.deepcopy(model)
-            m2.conv1.precision = 'f16x2'
-            m2.conv1.invalidate()
+            m2 = KernelNN(w, kw, T, 6, in_width=6, precision='f16x2').to(dev).eval()
+            m2.load_state_dict(model.state_dict())
 
             def step_x2(i):
                 m2.conv1._h_cache.clear()

@@ -49,6 +49,11 @@ struct GemmTcArgs {
   int a_split_nk;
   int c_split;
   int* overflow;       // counts 32-column pieces holding a value beyond the fp16 range (fp16 outputs only), or nullptr
+  // backward epilogues: mask != nullptr -> C[r, c] = mask16[r * mask_ld + c] > 0 ? acc : 0 (ReLU derivative taken
+  // from the stored 16-bit activation); out_f32 -> C is fp32 [M, ldc], plain stores, no conversion.
+  const uint16_t* mask;
+  int64_t mask_ld;
+  int out_f32;
   TraceBuf trace;
   unsigned int trace_seq;
 };
@@ -225,6 +230,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
               for (int q = 0; q < 4; ++q) f[q] = fmaxf(f[q], 0.f);
             }
+            if (a.mask != nullptr && row_ok) {
+              const uint2 mk = __ldg(reinterpret_cast<const uint2*>(a.mask + static_cast<int64_t>(row) * a.mask_ld + col0) + j4);
+              if ((mk.x & 0x7FFFu) == 0u) f[0] = 0.f;
+              if ((mk.x & 0x7FFF0000u) == 0u) f[1] = 0.f;
+              if ((mk.y & 0x7FFFu) == 0u) f[2] = 0.f;
+              if ((mk.y & 0x7FFF0000u) == 0u) f[3] = 0.f;
+            }
+            if (a.out_f32) {
+              if (row_ok)
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.C) + static_cast<int64_t>(row) * a.ldc + col0 + 4 * j4) =
+                    make_float4(f[0], f[1], f[2], f[3]);
+              continue;
+            }
             if (FMT == 0 && a.overflow != nullptr) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) vmax = fmaxf(vmax, fabsf(f[q]));
@@ -278,8 +296,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               st_global_v8(dst + 16, pk + 8);   // sectors, ncu r1a)
             }
           };
-          store_piece(packed, col0);
-          if (FMT == 0 && a.c_split) store_piece(packed_lo, col0 + a.N);
+          if (!a.out_f32) {
+            store_piece(packed, col0);
+            if (FMT == 0 && a.c_split) store_piece(packed_lo, col0 + a.N);
+          }
         }
         if (cc + 1 < kChunks) tmem_ld_wait();
       }
@@ -348,7 +368,8 @@ int tc_num_sms() { return g_num_sms; }
 
 int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a_row0, int M, int K, const void* B,
                    int N, const float* bias, int relu, void* C, int64_t ldc, cudaStream_t st, const PipeFlags* pf,
-                   int64_t chunk_rows_pad, int64_t c_row0, int split_flags, int* overflow) {
+                   int64_t chunk_rows_pad, int64_t c_row0, int split_flags, int* overflow, const void* mask,
+                   int64_t mask_ld, int out_f32) {
   if (M <= 0 || N <= 0) return NNCONV_OK;
   int s = tc_init();
   if (s != NNCONV_OK) return s;
@@ -358,7 +379,7 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
   NNC_REQUIRE(!(a_split || c_split) || prec != PREC_BF16, NNCONV_ERR_ARG, "gemm_tc: split operands are fp16 only");
   const int nmul = c_split ? 2 : 1;
   NNC_REQUIRE(K % 64 == 0 && N % 64 == 0 && K >= 64, NNCONV_ERR_ARG, "gemm_tc: K=%d N=%d must be multiples of 64", K, N);
-  NNC_REQUIRE(ldc % 16 == 0 && (reinterpret_cast<uintptr_t>(C) & 31) == 0, NNCONV_ERR_ARG,
+  NNC_REQUIRE((ldc % 16 == 0 || (out_f32 && ldc % 4 == 0)) && (reinterpret_cast<uintptr_t>(C) & 31) == 0, NNCONV_ERR_ARG,
               "gemm_tc: C must be 32-byte aligned with ldc a multiple of 16 elements");
   const int bf = prec == PREC_BF16;
   const bool small = pf && pf->small_footprint && N >= 128;
@@ -376,6 +397,11 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
   a.a_split_nk = a_split ? K / 192 : 0;
   a.c_split = c_split ? 1 : 0;
   a.overflow = (overflow != nullptr && !bf) ? overflow : nullptr;
+  a.mask = static_cast<const uint16_t*>(mask);
+  a.mask_ld = mask_ld;
+  a.out_f32 = out_f32;
+  NNC_REQUIRE(mask == nullptr || (mask_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(mask) & 7) == 0), NNCONV_ERR_ARG,
+              "gemm_tc: mask must be 8-byte aligned with mask_ld a multiple of 4");
   {
     TraceHandle th = trace_get();
     static unsigned int launch_seq = 0;
@@ -392,7 +418,7 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
                             ? ((c_row0 + M + 31) / 32 * 32 <= chunk_rows_pad &&
                                static_cast<int64_t>(nmul * N / 64) * chunk_rows_pad < (int64_t(1) << 31))
                             : ldc == static_cast<int64_t>(nmul) * N;
-  if (!no_tma_store && pf == nullptr && panel_ok) {
+  if (!no_tma_store && pf == nullptr && panel_ok && !out_f32) {
     if (chunk_rows_pad > 0) {
       s = make_tmap_store_16b(&tmC, bf, C, static_cast<uint64_t>(nmul * N / 64) * static_cast<uint64_t>(chunk_rows_pad), 64);
     } else {

@@ -53,7 +53,13 @@ enum { GEMM_A_SPLIT = 1, GEMM_C_SPLIT = 2 };
 int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a_row0, int M, int K,
                    const void* B, int N, const float* bias, int relu, void* C, int64_t ldc, cudaStream_t st,
                    const PipeFlags* pf = nullptr, int64_t chunk_rows_pad = 0, int64_t c_row0 = 0,
-                   int split_flags = 0, int* overflow = nullptr);
+                   int split_flags = 0, int* overflow = nullptr, const void* mask = nullptr, int64_t mask_ld = 0,
+                   int out_f32 = 0);
+
+// ---- gemm_tn.cu (tcgen05, MN-major operands): C[M, N] fp32 += alpha * sum_{r<R} A[r, a_col0 + m] * B[r, b_col0 + n]
+// (A: [R, lda], B: [R, ldb] 16-bit row-major; C accumulates with fp32 atomics, the caller zero-initialises it)
+int launch_gemm_tn(int prec, const void* A, int64_t lda, int a_col0, const void* B, int64_t ldb, int b_col0, int64_t R,
+                   int M, int N, float* C, int64_t ldc, float alpha, const float* alpha_dev, cudaStream_t st);
 
 // ---- conv_tc.cu (tcgen05): per-source contraction + scatter for tiles [tile_begin, tile_end)
 int launch_conv_tc(int prec, const Plan* P, const void* h, int Kp, const void* Y, int64_t y_nodes, int cout,
