@@ -25,6 +25,8 @@ SYMBOLS = [
     'nnconv_profile_begin', 'nnconv_profile_end', 'nnconv_debug_trace_dump',
     'nnconv_backward_sizes', 'nnconv_backward',
     'nnconv_set_option', 'nnconv_get_option', 'nnconv_edge_features_overflow', 'nnconv_debug_occupy',
+    'nnconv_backward_tc_supported', 'nnconv_backward_apply_sizes', 'nnconv_backward_apply',
+    'nnconv_backward_mlp_sizes', 'nnconv_backward_mlp', 'nnconv_gemm_tn_16b', 'nnconv_gemm_16b_ex',
 ]
 
 
@@ -86,6 +88,17 @@ def lib():
     L.nnconv_get_option.argtypes = [ctypes.c_char_p, P(c_int)]
     L.nnconv_edge_features_overflow.argtypes = [c_vp, c_vp, P(c_i64)]
     L.nnconv_debug_occupy.argtypes = [c_int, c_int, ctypes.c_longlong, c_vp]
+    L.nnconv_backward_tc_supported.argtypes = [c_vp]
+    L.nnconv_backward_apply_sizes.argtypes = [c_vp, c_vp, c_sz, P(c_sz)]
+    L.nnconv_backward_apply.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                        c_sz, c_vp]
+    L.nnconv_backward_mlp_sizes.argtypes = [c_vp, c_vp, c_int, c_sz, P(c_sz)]
+    L.nnconv_backward_mlp.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, P(c_vp), P(c_vp), c_int, P(c_vp), P(c_vp), c_vp,
+                                      c_sz, c_vp]
+    L.nnconv_gemm_tn_16b.argtypes = [c_int, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_i64, ctypes.c_float,
+                                     c_vp]
+    L.nnconv_gemm_16b_ex.argtypes = [c_int, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_i64, c_vp, c_i64, c_int,
+                                     c_vp]
     for name in SYMBOLS:
         getattr(L, name)
     _lib = L

@@ -48,6 +48,8 @@ static size_t esize_of(int prec) { return prec == PREC_FP32 ? 4 : 2; }
 // ------------------------------------------------------------------------------------------------
 struct WeightsLayout {
   size_t off_W1, off_b1, off_W1aug, off_Wh[kMaxLayers], off_bh[kMaxLayers], off_W3p, off_B3, bytes;
+  size_t off_W3q, off_W3t, off_WhT[kMaxLayers];
+  bool bwd;
 };
 
 static int fill_dims(Weights* W, int n_layers, const int* dims, int cin, int cout, int prec) {
@@ -93,6 +95,14 @@ static WeightsLayout layout_weights(const Weights* W) {
   }
   L.off_W3p = c.off; c.take<char>(static_cast<size_t>(W->cout) * W->Kp * W->cin_p * W->esize * (W->split ? 3 : 1));
   L.off_B3 = c.off; c.take<float>(static_cast<size_t>(W->cin) * W->cout);
+  // images for the tensor-core backward (same conditions as backward_tc_supported)
+  L.bwd = (W->prec == PREC_F16 || W->prec == PREC_BF16) && W->cout == 64 && W->cin <= 64 && nl >= 2 &&
+          3 * W->dims[0] + 2 <= 64;
+  if (L.bwd) {
+    L.off_W3q = c.off; c.take<char>(static_cast<size_t>(W->cout) * W->Kp * W->cin_p * 2);
+    L.off_W3t = c.off; c.take<char>(static_cast<size_t>(W->cout) * W->Kp * W->cin_p * 2);
+    for (int l = 2; l <= nl - 1; ++l) { L.off_WhT[l] = c.off; c.take<char>(static_cast<size_t>(W->kp[l]) * W->kp[l - 1] * 2); }
+  }
   L.bytes = c.off;
   return L;
 }
@@ -146,6 +156,19 @@ int weights_prepare(Weights* W, int n_layers, const int* dims, int cin, int cout
   if (s) return s;
   W->W3p = W3p;
   W->B3 = B3;
+  if (L.bwd) {
+    s = launch_w3q(prec, Wsrc[nl - 1], cin, cout, W->K, W->Kp, W->cin_p, 0, base + L.off_W3q, st);
+    if (s) return s;
+    s = launch_w3q(prec, Wsrc[nl - 1], cin, cout, W->K, W->Kp, W->cin_p, 1, base + L.off_W3t, st);
+    if (s) return s;
+    W->W3q = base + L.off_W3q;
+    W->W3t = base + L.off_W3t;
+    for (int l = 2; l <= nl - 1; ++l) {
+      s = launch_transpose_pad(prec, Wsrc[l - 1], dims[l], dims[l - 1], base + L.off_WhT[l], W->kp[l], W->kp[l - 1], st);
+      if (s) return s;
+      W->WhT[l] = base + L.off_WhT[l];
+    }
+  }
   return NNCONV_OK;
 }
 
@@ -630,6 +653,58 @@ int nnconv_backward(const nnconv_plan_t* plan, const nnconv_weights_t* w, const 
   NNC_REQUIRE((root == nullptr) == (grad_root == nullptr), NNCONV_ERR_ARG, "root / grad_root must both be given or both be NULL");
   return backward_fp32(&plan->p, &w->w, edge_attr, x, root, aggr == NNCONV_AGGR_MEAN, grad_out, grad_x, grad_W,
                        grad_b, grad_root, grad_bias, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int nnconv_backward_tc_supported(const nnconv_weights_t* w) { return w && backward_tc_supported(&w->w) ? 1 : 0; }
+
+int nnconv_backward_apply_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t want_bytes, size_t* ws_bytes) {
+  NNC_REQUIRE(plan && w && ws_bytes, NNCONV_ERR_ARG, "null pointer");
+  NNC_REQUIRE(backward_tc_supported(&w->w), NNCONV_ERR_UNSUPPORTED, "tensor-core backward: unsupported shape / precision");
+  *ws_bytes = backward_apply_ws_bytes(&plan->p, &w->w, want_bytes);
+  return NNCONV_OK;
+}
+
+int nnconv_backward_apply(const nnconv_plan_t* plan, const nnconv_weights_t* w, const void* h, const float* x,
+                          const float* root, int aggr, const float* grad_out, float* grad_x, float* grad_W_last,
+                          float* grad_b_last, float* grad_root, float* grad_bias, void* ws, size_t ws_bytes,
+                          void* stream) {
+  NNC_REQUIRE(plan && w && x && grad_out && grad_x && grad_W_last && grad_b_last && (h || plan->p.E == 0), NNCONV_ERR_ARG,
+              "null pointer");
+  NNC_REQUIRE(aggr == NNCONV_AGGR_ADD || aggr == NNCONV_AGGR_MEAN, NNCONV_ERR_UNSUPPORTED, "aggr must be add or mean");
+  NNC_REQUIRE((root == nullptr) == (grad_root == nullptr), NNCONV_ERR_ARG, "root / grad_root must both be given or both be NULL");
+  return backward_apply_tc(&plan->p, &w->w, h, x, root, aggr == NNCONV_AGGR_MEAN, grad_out, grad_x, grad_W_last,
+                           grad_b_last, grad_root, grad_bias, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int nnconv_backward_mlp_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, int n_apps, size_t want_bytes,
+                              size_t* ws_bytes) {
+  NNC_REQUIRE(plan && w && ws_bytes && n_apps >= 1, NNCONV_ERR_ARG, "bad arguments");
+  NNC_REQUIRE(backward_tc_supported(&w->w), NNCONV_ERR_UNSUPPORTED, "tensor-core backward: unsupported shape / precision");
+  *ws_bytes = backward_mlp_ws_bytes(&plan->p, &w->w, n_apps, want_bytes);
+  return NNCONV_OK;
+}
+
+int nnconv_backward_mlp(const nnconv_plan_t* plan, const nnconv_weights_t* w, const float* edge_attr, const void* h,
+                        int n_apps, const float* const* grad_out, const float* const* x, int aggr, float* const* grad_W,
+                        float* const* grad_b, void* ws, size_t ws_bytes, void* stream) {
+  NNC_REQUIRE(plan && w && grad_out && x && grad_W && grad_b && ((edge_attr && h) || plan->p.E == 0), NNCONV_ERR_ARG,
+              "null pointer");
+  NNC_REQUIRE(aggr == NNCONV_AGGR_ADD || aggr == NNCONV_AGGR_MEAN, NNCONV_ERR_UNSUPPORTED, "aggr must be add or mean");
+  return backward_mlp_tc(&plan->p, &w->w, edge_attr, h, n_apps, grad_out, x, aggr == NNCONV_AGGR_MEAN, grad_W, grad_b, ws,
+                         ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int nnconv_gemm_tn_16b(int precision, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t R, int M, int N,
+                       float* C, int64_t ldc, float alpha, void* stream) {
+  NNC_REQUIRE(A && B && C, NNCONV_ERR_ARG, "gemm_tn: null pointer");
+  return launch_gemm_tn(precision, A, lda, 0, B, ldb, 0, R, M, N, C, ldc, alpha, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int nnconv_gemm_16b_ex(int precision, const void* A, int64_t M, int K, const void* B, int N, const float* bias, int relu,
+                       void* C, int64_t ldc, const void* mask, int64_t mask_ld, int out_f32, void* stream) {
+  NNC_REQUIRE(A && B && C && M >= 1 && M < (int64_t(1) << 31), NNCONV_ERR_ARG, "gemm: bad arguments");
+  return launch_gemm_tc(precision, A, M, 0, static_cast<int>(M), K, B, N, bias, relu, C, ldc,
+                        static_cast<cudaStream_t>(stream), nullptr, 0, 0, 0, nullptr, mask, mask_ld, out_f32);
 }
 
 int nnconv_profile_begin(void) {

@@ -22,6 +22,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "kernels.h"
 #include "tc05.cuh"
 #include "tmap.h"
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(256) k_gather_g16(const float* __restrict__ g,
       const float sc = (inv_deg ? inv_deg[d] : 1.f) * inv_gs;
       const float4 a = *reinterpret_cast<const float4*>(g + static_cast<int64_t>(d) * 64 + c0);
       const float4 b = *reinterpret_cast<const float4*>(g + static_cast<int64_t>(d) * 64 + c0 + 4);
-      if (sizeof(T16) == 2 && std::is_same<T16, __half>::value) {
+      if (std::is_same<T16, __half>::value) {
         w[0] = pack2<0>(a.x * sc, a.y * sc); w[1] = pack2<0>(a.z * sc, a.w * sc);
         w[2] = pack2<0>(b.x * sc, b.y * sc); w[3] = pack2<0>(b.z * sc, b.w * sc);
       } else {
@@ -223,7 +225,7 @@ __global__ void k_prep_xg(const float* __restrict__ x, const int* __restrict__ s
   if (i >= static_cast<int64_t>(S) * cin_p) return;
   const int c = static_cast<int>(i / cin_p), ii = static_cast<int>(i % cin_p);
   const float v = ii < cin ? x[static_cast<int64_t>(src_nodes[c]) * cin + ii] * scal[5] : 0.f;
-  if (std::is_same<T16, __half>::value) Xg[i] = __float2half_rn(v);
+  if (std::is_same<T16, __half>::value) reinterpret_cast<__half*>(Xg)[i] = __float2half_rn(v);
   else reinterpret_cast<__nv_bfloat16*>(Xg)[i] = __float2bfloat16_rn(v);
 }
 
@@ -917,8 +919,6 @@ int backward_mlp_tc(const Plan* P, const Weights* W, const float* edge_attr, con
   }
   const int dh_smem = T * kDhAChunk + kDhBStages * BN * 128 + 1024;
   NNC_REQUIRE(dh_smem <= 227 * 1024, NNCONV_ERR_UNSUPPORTED, "backward_mlp: T=%d applications do not fit shared memory", T);
-  Maps8 tmHunused;
-  (void)tmHunused;
   int c0 = 0;
   while (c0 < S) {
     int c1 = c0;

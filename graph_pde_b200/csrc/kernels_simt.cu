@@ -47,6 +47,31 @@ __global__ void k_w3p(const float* __restrict__ WL, int cin, int cout, int K, in
   dst[idx] = cvt<T>(v);
 }
 
+// W3q[(k*cout + o) * cin_p + i] = W_L[(i*cout + o) * K + k]  /  W3t[i * (Kp*cout) + (k*cout + o)] = same
+template <typename T>
+__global__ void k_w3q(const float* __restrict__ WL, int cin, int cout, int K, int Kp, int cin_p, int transposed,
+                      T* __restrict__ dst) {
+  int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t NY = static_cast<int64_t>(Kp) * cout;
+  if (idx >= NY * cin_p) return;
+  int i;
+  int64_t ko;
+  if (transposed) { i = static_cast<int>(idx / NY); ko = idx % NY; }
+  else { i = static_cast<int>(idx % cin_p); ko = idx / cin_p; }
+  const int o = static_cast<int>(ko % cout), k = static_cast<int>(ko / cout);
+  const float v = (i < cin && k < K) ? WL[(static_cast<int64_t>(i) * cout + o) * K + k] : 0.f;
+  dst[idx] = cvt<T>(v);
+}
+
+// dst[c, r] (Cp x Rp) = src[r, c] (R x C), zero padded
+template <typename T>
+__global__ void k_transpose_pad(const float* __restrict__ src, int R, int C, T* __restrict__ dst, int Rp, int Cp) {
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<int64_t>(Rp) * Cp) return;
+  const int c = static_cast<int>(i / Rp), r = static_cast<int>(i % Rp);
+  dst[i] = cvt<T>((r < R && c < C) ? src[static_cast<int64_t>(r) * C + c] : 0.f);
+}
+
 // ---- PREC_F16X2 weight images: K is tripled, [hi(W) | lo(W) | hi(W)], to pair with activations read as
 // [hi(a) | hi(a) | lo(a)]:  a.W ~= hi*hi + hi*lo + lo*hi  (the dropped lo*lo term is 2^-22 relative)
 __device__ __forceinline__ __half split_part(float v, int part) {
@@ -394,6 +419,25 @@ int launch_w3p(int prec, const float* WL, int cin, int cout, int K, int Kp, int 
   if (prec == PREC_FP32) k_w3p<float><<<g, 256, 0, st>>>(WL, cin, cout, K, Kp, cin_p, static_cast<float*>(dst));
   else if (prec == PREC_F16) k_w3p<__half><<<g, 256, 0, st>>>(WL, cin, cout, K, Kp, cin_p, static_cast<__half*>(dst));
   else k_w3p<__nv_bfloat16><<<g, 256, 0, st>>>(WL, cin, cout, K, Kp, cin_p, static_cast<__nv_bfloat16*>(dst));
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
+}
+
+int launch_w3q(int prec, const float* WL, int cin, int cout, int K, int Kp, int cin_p, int transposed, void* dst,
+               cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(cout) * Kp * cin_p;
+  const unsigned g = (unsigned)ceil_div64(total, 256);
+  if (prec == PREC_F16) k_w3q<__half><<<g, 256, 0, st>>>(WL, cin, cout, K, Kp, cin_p, transposed, static_cast<__half*>(dst));
+  else k_w3q<__nv_bfloat16><<<g, 256, 0, st>>>(WL, cin, cout, K, Kp, cin_p, transposed, static_cast<__nv_bfloat16*>(dst));
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
+}
+
+int launch_transpose_pad(int prec, const float* src, int R, int C, void* dst, int Rp, int Cp, cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(Rp) * Cp;
+  const unsigned g = (unsigned)ceil_div64(total, 256);
+  if (prec == PREC_F16) k_transpose_pad<__half><<<g, 256, 0, st>>>(src, R, C, static_cast<__half*>(dst), Rp, Cp);
+  else k_transpose_pad<__nv_bfloat16><<<g, 256, 0, st>>>(src, R, C, static_cast<__nv_bfloat16*>(dst), Rp, Cp);
   NNC_CHECK_LAUNCH();
   return NNCONV_OK;
 }

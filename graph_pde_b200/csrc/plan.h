@@ -60,6 +60,10 @@ struct Weights {
   const float* bh[kMaxLayers];  // [kp[l]] fp32
   const void* W3p;              // [cout*Kp, cin_p] in `prec`:  W3p[(o*Kp + k), i] = W_L[i*cout + o, k] (split: 3*cin_p columns)
   const float* B3;              // [cin, cout] fp32 = b_L viewed (in, out)
+  // extra images for the tensor-core backward (16-bit, non-split precisions only; nullptr otherwise)
+  const void* W3q;              // [Kp*cout, cin_p]:  W3q[(k*cout + o), i] = W_L[i*cout + o, k]   (Y^T rows per source)
+  const void* W3t;              // [cin_p, Kp*cout]:  W3t[i, (k*cout + o)] = W_L[i*cout + o, k]   (dx = dY : W_L)
+  const void* WhT[kMaxLayers];  // hidden layers l = 2 .. L-1 transposed: [kp[l-1], kp[l]]       (dz_{l-1} = dz_l W_l)
 };
 
 size_t weights_bytes(int n_layers, const int* dims, int cin, int cout, int prec);
@@ -76,6 +80,18 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
 size_t apply_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes);
 int apply(const Plan* P, const Weights* W, const void* h, const float* x, const float* root, const float* bias,
           int aggr_mean, float* out, void* ws, size_t ws_bytes, cudaStream_t st, int64_t* launches);
+
+// tensor-core backward (backward_tc.cu): per application (dx, dW_L, db_L, droot, dbias) and, once per
+// (edge_attr, parameters) for all T applications of a shared conv, the pass through the hidden layers
+bool backward_tc_supported(const Weights* W);
+size_t backward_apply_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes);
+int backward_apply_tc(const Plan* P, const Weights* W, const void* h, const float* x, const float* root,
+                      int aggr_mean, const float* gout, float* dx, float* dWL, float* dbL, float* droot, float* dbias,
+                      void* ws, size_t ws_bytes, cudaStream_t st);
+size_t backward_mlp_ws_bytes(const Plan* P, const Weights* W, int T, size_t want_bytes);
+int backward_mlp_tc(const Plan* P, const Weights* W, const float* edge_attr, const void* h, int T,
+                    const float* const* gouts, const float* const* xs_in, int aggr_mean, float* const* dWs,
+                    float* const* dbs, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // backward of one application (fp32 CUDA-core path), backward.cu
 size_t backward_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes);

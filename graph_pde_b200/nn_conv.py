@@ -41,7 +41,12 @@ _PLAN_CACHE_MAX_BYTES = int(os.environ.get('NNCONV_B200_PLAN_CACHE_BYTES', str(2
 _OVERFLOW_CHECK = os.environ.get('NNCONV_B200_OVERFLOW_CHECK', '1') != '0'
 _Y_BYTES = int(os.environ.get('NNCONV_B200_Y_BYTES', str(48 << 20)))       # Y ring: 3 x 128 sources at out=64, Kp=1024
 _EF_WS_BYTES = int(os.environ.get('NNCONV_B200_EF_WS_BYTES', str(4 << 30)))  # hidden-layer ping-pong chunk (4 GiB: 25 instead of 97 chunks at 241^2, -1 ms/step, run39)
-_BWD_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_WS_BYTES', str(2 << 30)))  # backward: activations per batch
+_BWD_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_WS_BYTES', str(2 << 30)))  # fp32 backward: activations per batch
+# tensor-core backward: per-application workspace (dY of a source batch: 7.6 GB covers 241^2 in one batch) and the
+# per-batch buffers of the deferred pass through the hidden layers
+_BWD_APPLY_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_APPLY_WS_BYTES', str(9 << 30)))
+_BWD_MLP_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_MLP_WS_BYTES', str(6 << 30)))
+_BWD_MODE = os.environ.get('NNCONV_B200_BACKWARD', 'auto')       # auto | tc | fp32
 
 
 def default_precision():
@@ -171,15 +176,17 @@ class _Prepared(object):
         self.dims = dims
         self.precision = precision
         self.tc = bool(L.nnconv_weights_tc_supported(h))
+        self.bwd_tc = bool(L.nnconv_backward_tc_supported(h))
         stats['weight_preps'] += 1
         stats['launches'] += 2 * n + 1
         self._finalizer = weakref.finalize(self, L.nnconv_weights_destroy, h)
 
 
 class _NNConvFunction(torch.autograd.Function):
-    """Differentiable wrapper: forward = the configured precision path, backward = nnconv_backward (fp32
-    CUDA-core kernels, csrc/backward.cu).  Gradients flow to x, the edge-MLP Linear weights/biases, root and
-    bias; edge_index / edge_attr are leaf inputs in every reference script and get none."""
+    """Differentiable wrapper, CUDA-core variant: forward = the configured precision path, backward =
+    nnconv_backward (fp32 CUDA-core kernels, csrc/backward.cu; any shape, activations recomputed).  Gradients flow
+    to x, the edge-MLP Linear weights/biases, root and bias; edge_index / edge_attr are leaf inputs in every
+    reference script and get none."""
 
     @staticmethod
     def forward(ctx, module, x, edge_index, edge_attr, *params):
@@ -197,6 +204,60 @@ class _NNConvFunction(torch.autograd.Function):
         by_id = {id(p): g for p, g in grads['params']}
         return (None, grads['x'] if ctx.needs_input_grad[1] else None, None, None) + tuple(
             by_id.get(id(p)) for p in module.parameters())
+
+
+class _TrainState(object):
+    """What the tensor-core backward shares between the applications of one conv on one (edge_attr, parameters):
+    the plan, the prepared weights, the cached edge features and, filled during the backward sweep, every
+    application's (grad_out, x) for the ONE deferred pass through the hidden layers."""
+
+    def __init__(self, key, plan, prepared, h, ea32):
+        self.key, self.plan, self.prepared, self.h, self.ea32 = key, plan, prepared, h, ea32
+        self.apps = []
+        self.consumed = False
+        self.token = None
+
+
+class _EdgeFeaturesFn(torch.autograd.Function):
+    """Autograd node of the x-independent part h = MLP_without_last_Linear(edge_attr).  Its output is a 1-element
+    token (h itself lives in the module's cache: 2 KB per edge): every application's backward returns a dummy
+    gradient for the token, so autograd runs THIS backward exactly once, after all of them -- with every
+    (grad_out, x) pair collected in the state, the hidden layers are differentiated once for all T applications."""
+
+    @staticmethod
+    def forward(ctx, module, state, *hidden_params):
+        ctx.module, ctx.state = module, state
+        return torch.zeros(1, device=state.h.device)
+
+    @staticmethod
+    def backward(ctx, _):
+        state = ctx.state
+        grads = ctx.module._backward_mlp_impl(state)
+        state.consumed = True
+        state.apps = []
+        return (None, None) + tuple(grads)
+
+
+class _ApplyFn(torch.autograd.Function):
+    """One NNConv application given the edge features (tensor-core forward and backward)."""
+
+    @staticmethod
+    def forward(ctx, module, state, x, token, w_last, b_last, root, bias):
+        ctx.module, ctx.state = module, state
+        x32 = x.detach().contiguous().float()
+        ctx.save_for_backward(x32)
+        ctx.x_dtype = x.dtype
+        return module._apply_impl(state.plan, state.prepared, state.h, x32)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (x32,) = ctx.saved_tensors
+        module, state = ctx.module, ctx.state
+        g32 = grad_out.detach().contiguous().float()
+        dx, dwl, dbl, droot, dbias = module._backward_apply_impl(state, x32, g32)
+        state.apps.append((g32, x32))
+        return (None, None, dx.to(ctx.x_dtype) if ctx.needs_input_grad[2] else None, torch.zeros_like(state.token),
+                dwl, dbl, droot, dbias)
 
 
 class NNConv_old(torch.nn.Module):
@@ -267,6 +328,10 @@ class NNConv_old(torch.nn.Module):
         if needs_grad:
             if self.aggr == 'max':
                 raise NotImplementedError("aggr='max' is used by no call site of the reference and is not built")
+            state = self._train_state(x, edge_index, pseudo)
+            if state is not None:            # tensor-core backward (csrc/backward_tc.cu)
+                lin = _linear_chain(self.nn)[-1]
+                return _ApplyFn.apply(self, state, x, state.token, lin.weight, lin.bias, self.root, self.bias)
             return _NNConvFunction.apply(self, x, edge_index, pseudo, *list(self.parameters()))
         return self._forward_impl(x, edge_index, pseudo)
 
@@ -333,7 +398,7 @@ class NNConv_old(torch.nn.Module):
         self._h_cache[key] = (h, edge_attr)          # hold edge_attr so its address cannot be recycled
         return h
 
-    def _forward_impl(self, x, edge_index, pseudo):
+    def _check_inputs(self, x, edge_index, pseudo):
         _require_cuda(x, 'x')
         _require_cuda(edge_index, 'edge_index')
         _require_cuda(pseudo, 'edge_attr')
@@ -345,31 +410,117 @@ class NNConv_old(torch.nn.Module):
             raise ValueError('x has %d channels, expected %d' % (x.size(1), self.in_channels))
         if pseudo.size(0) != edge_index.size(1):
             raise ValueError('edge_attr has %d rows for %d edges' % (pseudo.size(0), edge_index.size(1)))
+
+    def _prepare(self, x, edge_index, pseudo):
+        """plan, prepared weights, fp32 edge_attr and the (cached) edge features for this call."""
         precision = self.precision or default_precision()
-        with torch.cuda.device(x.device):
-            x32 = x.detach().contiguous().float()
-            ea32 = pseudo.detach()
-            if ea32.dtype != torch.float32 or not ea32.is_contiguous():
-                ea32 = ea32.contiguous().float()
-            n = x32.size(0)
-            plan = get_plan(edge_index, n, self.flow)
-            prepared = self._get_prepared(precision)
-            h = self.edge_features(plan, prepared, ea32)
-            L = _lib.lib()
-            ws_b = ctypes.c_size_t()
-            _lib.check(L.nnconv_apply_sizes(plan.handle, prepared.handle, _Y_BYTES, ctypes.byref(ws_b)))
-            ws = torch.empty(ws_b.value, dtype=torch.uint8, device=x.device)
-            out = torch.empty(n, self.out_channels, dtype=torch.float32, device=x.device)
-            root = self.root.detach().contiguous().float() if self.root is not None else None
-            bias = self.bias.detach().contiguous().float() if self.bias is not None else None
-            n_l = ctypes.c_int64(0)
-            _lib.check(L.nnconv_apply(plan.handle, prepared.handle, _ptr(h), _ptr(x32), _ptr(root), _ptr(bias),
-                                      _lib.AGGR[self.aggr], _ptr(out), _ptr(ws), ws_b.value, _stream_ptr(x.device),
-                                      ctypes.byref(n_l)))
-            stats['launches'] += n_l.value
-            stats['applies'] += 1
+        ea32 = pseudo.detach()
+        if ea32.dtype != torch.float32 or not ea32.is_contiguous():
+            ea32 = ea32.contiguous().float()
+        plan = get_plan(edge_index, x.size(0), self.flow)
+        prepared = self._get_prepared(precision)
+        h = self.edge_features(plan, prepared, ea32)
+        return plan, prepared, ea32, h
+
+    def _apply_impl(self, plan, prepared, h, x32):
+        L = _lib.lib()
+        dev = x32.device
+        ws_b = ctypes.c_size_t()
+        _lib.check(L.nnconv_apply_sizes(plan.handle, prepared.handle, _Y_BYTES, ctypes.byref(ws_b)))
+        ws = torch.empty(ws_b.value, dtype=torch.uint8, device=dev)
+        out = torch.empty(x32.size(0), self.out_channels, dtype=torch.float32, device=dev)
+        root = self.root.detach().contiguous().float() if self.root is not None else None
+        bias = self.bias.detach().contiguous().float() if self.bias is not None else None
+        n_l = ctypes.c_int64(0)
+        _lib.check(L.nnconv_apply(plan.handle, prepared.handle, _ptr(h), _ptr(x32), _ptr(root), _ptr(bias),
+                                  _lib.AGGR[self.aggr], _ptr(out), _ptr(ws), ws_b.value, _stream_ptr(dev),
+                                  ctypes.byref(n_l)))
+        stats['launches'] += n_l.value
+        stats['applies'] += 1
         return out
 
+    def _forward_impl(self, x, edge_index, pseudo):
+        self._check_inputs(x, edge_index, pseudo)
+        with torch.cuda.device(x.device):
+            x32 = x.detach().contiguous().float()
+            plan, prepared, _, h = self._prepare(x32, edge_index, pseudo)
+            return self._apply_impl(plan, prepared, h, x32)
+
+    # -- tensor-core training path ----------------------------------------------------------------------
+    def _train_state(self, x, edge_index, pseudo):
+        """State shared by the applications of this conv on (edge_attr, parameters), or None when the tensor-core
+        backward does not cover the configuration (the fp32 CUDA-core backward is used then)."""
+        mode = _BWD_MODE
+        if mode == 'fp32' or pseudo.requires_grad:
+            return None
+        self._check_inputs(x, edge_index, pseudo)
+        with torch.cuda.device(x.device):
+            plan, prepared, ea32, h = self._prepare(x, edge_index, pseudo)
+            if not prepared.bwd_tc:
+                if mode == 'tc':
+                    raise NotImplementedError('NNCONV_B200_BACKWARD=tc: shape / precision not covered by the tensor-core backward')
+                return None
+            key = (plan.key, ea32.data_ptr(), tuple(ea32.shape), ea32._version, id(prepared))
+            st = getattr(self, '_tstate', None)
+            if st is None or st.key != key or st.consumed or st.h is not h:
+                st = _TrainState(key, plan, prepared, h, ea32)
+                hidden = []
+                for l in _linear_chain(self.nn)[:-1]:
+                    hidden += [l.weight, l.bias]
+                st.token = _EdgeFeaturesFn.apply(self, st, *hidden)
+                self._tstate = st
+            return st
+
+    def _backward_apply_impl(self, state, x32, g32):
+        L = _lib.lib()
+        dev = x32.device
+        plan, prep = state.plan, state.prepared
+        lin = _linear_chain(self.nn)[-1]
+        with torch.cuda.device(dev):
+            ws_b = ctypes.c_size_t()
+            _lib.check(L.nnconv_backward_apply_sizes(plan.handle, prep.handle, _BWD_APPLY_WS_BYTES, ctypes.byref(ws_b)))
+            ws = torch.empty(ws_b.value, dtype=torch.uint8, device=dev)
+            dx = torch.empty_like(x32)
+            dwl = torch.empty_like(lin.weight, dtype=torch.float32)
+            dbl = torch.empty_like(lin.bias, dtype=torch.float32)
+            droot = torch.empty_like(self.root, dtype=torch.float32) if self.root is not None else None
+            dbias = torch.empty_like(self.bias, dtype=torch.float32) if self.bias is not None else None
+            root = self.root.detach().contiguous().float() if self.root is not None else None
+            _lib.check(L.nnconv_backward_apply(plan.handle, prep.handle, _ptr(state.h), _ptr(x32), _ptr(root),
+                                               _lib.AGGR[self.aggr], _ptr(g32), _ptr(dx), _ptr(dwl), _ptr(dbl),
+                                               _ptr(droot), _ptr(dbias), _ptr(ws), ws_b.value, _stream_ptr(dev)))
+            stats['backwards'] = stats.get('backwards', 0) + 1
+        return dx, dwl, dbl, droot, dbias
+
+    def _backward_mlp_impl(self, state):
+        """Gradients of the hidden Linear layers, one pass for all applications recorded in the state (in groups
+        of <= 6 when a conv is applied more often)."""
+        L = _lib.lib()
+        plan, prep = state.plan, state.prepared
+        hidden = _linear_chain(self.nn)[:-1]
+        dev = state.h.device
+        total = None
+        with torch.cuda.device(dev):
+            for i0 in range(0, len(state.apps), 6):
+                apps = state.apps[i0:i0 + 6]
+                n = len(apps)
+                ws_b = ctypes.c_size_t()
+                _lib.check(L.nnconv_backward_mlp_sizes(plan.handle, prep.handle, n, _BWD_MLP_WS_BYTES, ctypes.byref(ws_b)))
+                ws = torch.empty(ws_b.value, dtype=torch.uint8, device=dev)
+                dws = [torch.empty_like(l.weight, dtype=torch.float32) for l in hidden]
+                dbs = [torch.empty_like(l.bias, dtype=torch.float32) for l in hidden]
+                gp = (ctypes.c_void_p * n)(*[g.data_ptr() for g, _ in apps])
+                xp = (ctypes.c_void_p * n)(*[x.data_ptr() for _, x in apps])
+                wp = (ctypes.c_void_p * len(hidden))(*[t.data_ptr() for t in dws])
+                bp = (ctypes.c_void_p * len(hidden))(*[t.data_ptr() for t in dbs])
+                _lib.check(L.nnconv_backward_mlp(plan.handle, prep.handle, _ptr(state.ea32), _ptr(state.h), n, gp, xp,
+                                                 _lib.AGGR[self.aggr], wp, bp, _ptr(ws), ws_b.value, _stream_ptr(dev)))
+                flat = [t for pair in zip(dws, dbs) for t in pair]
+                total = flat if total is None else [a + b for a, b in zip(total, flat)]
+            stats['mlp_backwards'] = stats.get('mlp_backwards', 0) + 1
+        if total is None:     # no application contributed (cannot happen through autograd, kept for safety)
+            total = [torch.zeros_like(p, dtype=torch.float32) for l in hidden for p in (l.weight, l.bias)]
+        return total
 
     def _backward_impl(self, x, edge_index, pseudo, grad_out):
         if pseudo.requires_grad:

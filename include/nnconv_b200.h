@@ -132,6 +132,29 @@ int nnconv_backward(const nnconv_plan_t* plan, const nnconv_weights_t* w, const 
                     float* const* grad_b, float* grad_root, float* grad_bias, void* ws, size_t ws_bytes,
                     void* stream);
 
+/* ---- tensor-core backward (16-bit precisions, out_channels = 64, in_channels <= 64, edge MLP with >= 2 Linear
+ * layers; nnconv_backward_tc_supported tells).  Split in two because the edge features h do not depend on x:
+ *
+ *   nnconv_backward_apply   one call per application, given that application's grad_out: writes grad_x,
+ *                           grad of the LAST Linear (weight [in*out, K], bias [in*out]), grad_root, grad_bias.
+ *   nnconv_backward_mlp     ONE call per (edge_attr, parameters) after the n_apps applications that shared them
+ *                           (KernelNN applies one conv T times, UAI1_full_resolution.py:29-30): given every
+ *                           application's grad_out and x (HOST arrays of device pointers), writes the gradients of
+ *                           the hidden Linear layers 0 .. n_layers-2.  The reference's autograd runs this pass T times.
+ *
+ * `h` is the buffer nnconv_edge_features filled for the same (plan, w, edge_attr).  Gradients are WRITTEN. */
+int nnconv_backward_tc_supported(const nnconv_weights_t* w);
+int nnconv_backward_apply_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t want_bytes, size_t* ws_bytes);
+int nnconv_backward_apply(const nnconv_plan_t* plan, const nnconv_weights_t* w, const void* h, const float* x,
+                          const float* root, int aggr, const float* grad_out, float* grad_x, float* grad_W_last,
+                          float* grad_b_last, float* grad_root, float* grad_bias, void* ws, size_t ws_bytes,
+                          void* stream);
+int nnconv_backward_mlp_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, int n_apps, size_t want_bytes,
+                              size_t* ws_bytes);
+int nnconv_backward_mlp(const nnconv_plan_t* plan, const nnconv_weights_t* w, const float* edge_attr, const void* h,
+                        int n_apps, const float* const* grad_out, const float* const* x, int aggr, float* const* grad_W,
+                        float* const* grad_b, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- measurement hook (bench.py): while enabled, every kernel launch is bracketed by CUDA events on its
  * stream; profile_end synchronises the device and returns summed milliseconds / launch counts per kernel
  * class: 0 first MLP layer, 1 hidden-layer GEMM, 2 per-node prologue, 3 per-source Y GEMM (unfused path),
@@ -154,6 +177,14 @@ int nnconv_debug_occupy(int n_ctas, int smem_bytes, long long ns, void* stream);
  * C[M,N] (16-bit) = act(A[M,K] * B[N,K]^T + bias); K, N multiples of 64; bias nullable. ------------- */
 int nnconv_gemm_16b(int precision, const void* A, int64_t M, int K, const void* B, int N, const float* bias,
                     int relu, void* C, void* stream);
+
+/* ---- unit-test hooks for the backward GEMMs:
+ * gemm_tn:  C[M,N] (fp32, ACCUMULATED with atomics) += alpha * sum_{r<R} A[r,m] * B[r,n]   (A [R,lda], B [R,ldb] 16-bit)
+ * gemm_16b_ex: nnconv_gemm_16b with ldc, a ReLU-derivative mask (16-bit [M, mask_ld], keep where > 0) and fp32 output */
+int nnconv_gemm_tn_16b(int precision, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t R, int M, int N,
+                       float* C, int64_t ldc, float alpha, void* stream);
+int nnconv_gemm_16b_ex(int precision, const void* A, int64_t M, int K, const void* B, int N, const float* bias, int relu,
+                       void* C, int64_t ldc, const void* mask, int64_t mask_ld, int out_f32, void* stream);
 
 #ifdef __cplusplus
 }

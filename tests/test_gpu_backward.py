@@ -27,8 +27,10 @@ def _graph(gen, N, E, hub=False):
     ([3, 8 * 8], 8, 8, 'mean', True, False, 'fp32'),                # single Linear edge network
     ([6, 16, 32, 24, 64 * 64], 64, 64, 'mean', False, False, 'f16'),  # 4-layer MLP, MGKN style
 ])
-def test_backward_matches_autograd_through_oracle(layers, cin, cout, aggr, rw, bs, fwd_prec):
+def test_backward_matches_autograd_through_oracle(layers, cin, cout, aggr, rw, bs, fwd_prec, monkeypatch):
+    from graph_pde_b200 import nn_conv
     from graph_pde_b200.nn_conv import NNConv_old
+    monkeypatch.setattr(nn_conv, '_BWD_MODE', 'fp32')          # this file pins the CUDA-core fp32 backward
     gen = torch.Generator().manual_seed(17)
     N, E = 120, 1500
     ei = _graph(gen, N, E, hub=True)                 # unsorted sources + a hub with several tiles
@@ -72,7 +74,9 @@ def test_backward_matches_autograd_through_oracle(layers, cin, cout, aggr, rw, b
         chk('bias', conv.bias.grad, bbr.grad)
 
 
-def test_kernelnn_training_step_shares_gradients_over_T():
+def test_kernelnn_training_step_shares_gradients_over_T(monkeypatch):
+    from graph_pde_b200 import nn_conv
+    monkeypatch.setattr(nn_conv, '_BWD_MODE', 'fp32')
     """KernelNN applies ONE conv T times: parameter gradients must accumulate over the T applications
     (UAI1_full_resolution.py:29-30, loss.backward() :266)."""
     from graph_pde_b200.models import KernelNN
