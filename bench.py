@@ -242,6 +242,8 @@ def main():
     ap.add_argument('--precision', default=os.environ.get('NNCONV_B200_PRECISION', 'f16'))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-parity', action='store_true', help='skip the full-graph parity check and the fp32-grade line')
+    ap.add_argument('--no-train', action='store_true', help='skip the training-step measurement')
+    ap.add_argument('--no-strip', action='store_true', help='skip the single-mesh strip-partition measurement (N > 1)')
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', '0'))
@@ -385,6 +387,103 @@ def main():
         prof = {KIND_NAMES[k]: dict(ms=ms_k[k], launches=int(n_k[k])) for k in range(6)}
     barrier()
 
+    # ---- training step (forward + tensor-core backward + Adam), one graph sample per rank per step, parameter
+    # gradients sum-reduced over the ranks with ONE flat all-reduce (partition.allreduce_gradients; the reference's
+    # loss is a sum over the batch, UAI1_full_resolution.py:262-271).  Same timing rules as the main number.
+    train = None
+    if not args.no_train and args.precision in ('f16', 'bf16'):
+        from graph_pde_b200 import partition
+        model.conv1._h_cache.clear()
+        torch.cuda.empty_cache()
+        tmodel = KernelNN(w, kw, T, 6, in_width=6, precision=args.precision).to(dev)
+        tmodel.load_state_dict(model.state_dict())
+        opt = torch.optim.Adam(tmodel.parameters(), lr=1e-4)
+        targets = [torch.randn(N, 1, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + i + 10 * rank))
+                   for i in range(n_samples)]
+        n_params = sum(p.numel() for p in tmodel.parameters())
+        loss_hist = []
+
+        def step_train(i):
+            d = D()
+            d.x, d.edge_index, d.edge_attr = dev_x[i % n_samples], ei, dev_ea[i % n_samples]
+            opt.zero_grad(set_to_none=True)
+            out = tmodel(d)
+            loss = torch.norm(out.view(-1) - targets[i % n_samples].view(-1), 1)      # UAI1_full_resolution.py:265
+            loss.backward()
+            partition.allreduce_gradients(tmodel)
+            opt.step()
+            loss_hist.append(loss.detach())
+        tsteps = max(2, min(args.steps, 3))
+        ms_train = timed(step_train, tsteps, 2)
+        losses = [float(v) for v in loss_hist]
+        train = dict(value=world * E * T * tsteps / (ms_train * 1e-3), unit='edge-apps/s (forward + backward + Adam)',
+                     ms_per_step=ms_train / tsteps, steps=tsteps, warmup=2, n_gpus=world,
+                     allreduce_bytes_per_step=4 * n_params if world > 1 else 0, params=n_params,
+                     backward='tensor cores (csrc/backward_tc.cu): per-application k_dy + GEMMs, one deferred pass over the '
+                              'hidden layers for all T applications',
+                     loss_first=losses[0], loss_last=losses[-1],
+                     note='one 241^2-class graph per rank per step, L1 loss, Adam; gradients sum-reduced with one flat '
+                          'all-reduce per step' if world > 1 else 'one graph per step, L1 loss, Adam')
+        del tmodel, opt
+        torch.cuda.empty_cache()
+    barrier()
+
+    # ---- ONE mesh cut into N row strips (strong scaling; SURVEY 8(e) "single big mesh"): every rank owns the edges
+    # that END in its strip, computes their edge features, and the T applications exchange 2R boundary rows with the
+    # two neighbours by peer stores over NVLink (partition.PeerHalo, csrc/halo.cu) -- inside the timed region.
+    strip = None
+    if world > 1 and not args.no_strip:
+        from graph_pde_b200 import partition
+        model.conv1._h_cache.clear()
+        torch.cuda.empty_cache()
+        x6c, _, _ = graphs.darcy_sample(s, r, dev, seed=4242, edge_index=ei[:, :1])     # the SAME sample on every rank
+        part = partition.StripPartition(s, r, rank, world, device=dev)
+        grid = graphs.square_grid(s, dev)
+        ea_loc = graphs.ball_edge_attr(grid, part.edge_index_global, x6c[:, 2])
+        with torch.no_grad():
+            x0g = model.fc1(x6c)
+        x_loc = part.local_slice(x0g).clone()
+        mode = 'peer stores + flags (CUDA IPC over NVLink)'
+        try:
+            halo = partition.PeerHalo(part, w, dev)
+        except Exception as exc:                                   # e.g. IPC not permitted in this container
+            halo = None
+            mode = 'NCCL all-gather per application (peer mapping failed: %s)' % type(exc).__name__
+        ok_all = torch.tensor([1 if halo is not None else 0], device=dev)
+        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+        if int(ok_all.item()) == 0 and halo is not None:
+            halo, mode = None, 'NCCL all-gather per application (peer mapping failed on another rank)'
+        conv_fn = lambda xl, e, a: model.conv1(xl, e, a)          # noqa: E731
+
+        def step_strip(i):
+            model.conv1._h_cache.clear()
+            with torch.no_grad():
+                if halo is not None:
+                    return partition.partitioned_conv_stack_peer(conv_fn, x_loc, part, ea_loc, T, halo)
+                return partition.partitioned_conv_stack(conv_fn, x_loc.clone(), part, ea_loc, T)
+        ssteps = max(2, min(args.steps, 5))
+        ms_strip = timed(step_strip, ssteps, 3)
+        got = step_strip(0)
+        # parity against the unpartitioned stack on the same sample (every rank computes it: 1 step)
+        model.conv1._h_cache.clear()
+        torch.cuda.empty_cache()
+        with torch.no_grad():
+            ea_full = graphs.ball_edge_attr(grid, ei, x6c[:, 2])
+            full = model.conv_stack(x0g, ei, ea_full)
+        ref = full[part.row_lo * s:part.row_hi * s]
+        err = torch.tensor([float((got - ref).abs().max() / ref.abs().max())], device=dev)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        halo_bytes = 2 * part.R * s * w * 4 * (T - 1)
+        strip = dict(value=E * T * ssteps / (ms_strip * 1e-3), unit='edge-apps/s', scaling='strong', ms_per_step=ms_strip / ssteps,
+                     steps=ssteps, n_gpus=world, halo=mode, nvlink_bytes_per_rank_per_step=halo_bytes,
+                     local_edges=int(part.edge_index.size(1)), parity_vs_unpartitioned=float(err.item()),
+                     note='one %dx%d mesh (E=%d) cut into %d row strips, edges owned by their destination; a step = edge '
+                          'features of the local edges + T applications with a halo push after each' % (s, s, E, world))
+        del full, ea_full, got, halo
+        model.conv1._h_cache.clear()
+        torch.cuda.empty_cache()
+    barrier()
+
     # ---- parity at the benchmarked configuration and precision + the fp32-grade (f16x2) line, rank 0 only
     parity, fp32_grade = None, None
     if rank == 0 and not args.no_parity:
@@ -474,7 +573,7 @@ def main():
                                               'edge-app of the reference formulation; the hoisted/reassociated '
                                               'kernels execute ~40x fewer FLOPs, so formA_tensor_frac may exceed 1'
                                               % (f_alg, b_alg)),
-                    edges=E, nodes=N, parity=parity, fp32_grade=fp32_grade)
+                    edges=E, nodes=N, parity=parity, fp32_grade=fp32_grade, train=train, strip=strip)
         if not args.no_cpu_baseline:
             line['gpu_reference_port'] = gpu_reference_rate(cfg, dev)
             rate, cores, kind, desc, _ = cpu_reference_rate(cfg, steps=2)

@@ -27,6 +27,7 @@ SYMBOLS = [
     'nnconv_set_option', 'nnconv_get_option', 'nnconv_edge_features_overflow', 'nnconv_debug_occupy',
     'nnconv_backward_tc_supported', 'nnconv_backward_apply_sizes', 'nnconv_backward_apply',
     'nnconv_backward_mlp_sizes', 'nnconv_backward_mlp', 'nnconv_gemm_tn_16b', 'nnconv_gemm_16b_ex',
+    'nnconv_halo_push', 'nnconv_halo_wait', 'nnconv_loss_epilogue',
 ]
 
 
@@ -95,6 +96,11 @@ def lib():
     L.nnconv_backward_mlp_sizes.argtypes = [c_vp, c_vp, c_int, c_sz, P(c_sz)]
     L.nnconv_backward_mlp.argtypes = [c_vp, c_vp, c_vp, c_vp, c_int, P(c_vp), P(c_vp), c_int, P(c_vp), P(c_vp), c_vp,
                                       c_sz, c_vp]
+    L.nnconv_halo_push.argtypes = [c_vp, c_int, c_i64, c_int, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64,
+                                   c_i64, c_i64, c_vp, c_vp, c_int, c_vp]
+    L.nnconv_halo_wait.argtypes = [c_vp, c_vp, c_int, c_vp]
+    L.nnconv_loss_epilogue.argtypes = [c_vp, c_vp, c_vp, c_vp, ctypes.c_float, c_int, c_i64, ctypes.c_float, c_vp, c_vp,
+                                       c_vp, c_vp]
     L.nnconv_gemm_tn_16b.argtypes = [c_int, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_i64, ctypes.c_float,
                                      c_vp]
     L.nnconv_gemm_16b_ex.argtypes = [c_int, c_vp, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_i64, c_vp, c_i64, c_int,

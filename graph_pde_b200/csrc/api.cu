@@ -707,6 +707,23 @@ int nnconv_gemm_16b_ex(int precision, const void* A, int64_t M, int K, const voi
                         static_cast<cudaStream_t>(stream), nullptr, 0, 0, 0, nullptr, mask, mask_ld, out_f32);
 }
 
+int nnconv_halo_push(const float* out, int relu, int64_t n_local, int channels, int64_t own_lo, int64_t own_hi,
+                     float* x_next, float* peer_up, int64_t up_src0, int64_t up_dst0, int64_t up_rows, float* peer_down,
+                     int64_t dn_src0, int64_t dn_dst0, int64_t dn_rows, int* flag_up, int* flag_down, int seq,
+                     void* stream) {
+  return halo_push(out, relu, n_local, channels, own_lo, own_hi, x_next, peer_up, up_src0, up_dst0, up_rows, peer_down,
+                   dn_src0, dn_dst0, dn_rows, flag_up, flag_down, seq, static_cast<cudaStream_t>(stream));
+}
+
+int nnconv_halo_wait(const int* flag_from_up, const int* flag_from_down, int seq, void* stream) {
+  return halo_wait(flag_from_up, flag_from_down, seq, static_cast<cudaStream_t>(stream));
+}
+
+int nnconv_loss_epilogue(const float* out, const float* y, const float* mean, const float* std_, float eps, int batch,
+                         int64_t n, float grad_scale, float* grad_l1, float* results, float* ws, void* stream) {
+  return loss_epilogue(out, y, mean, std_, eps, batch, n, grad_scale, grad_l1, results, ws, static_cast<cudaStream_t>(stream));
+}
+
 int nnconv_profile_begin(void) {
   for (auto& r : nnc::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   nnc::g_prof.clear();

@@ -75,7 +75,13 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kStoreBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N, int FMT, int SMALL>
+// EPI selects the epilogue at COMPILE time (runtime flags inside the 32-column inner loop cut it into dozens of
+// tiny basic blocks and the K = 64 first-layer GEMM, which is epilogue bound, ran 2.4x slower: run r2b):
+//   EPI_PLAIN bias / ReLU / 16-bit store     EPI_SPLIT the same, written as (hi, lo) fp16 pairs (PREC_F16X2)
+//   EPI_MASK  ReLU-derivative mask from a stored activation (backward)     EPI_F32 fp32 output, plain stores
+enum { EPI_PLAIN = 0, EPI_SPLIT = 1, EPI_MASK = 2, EPI_F32 = 3 };
+
+template <int BLOCK_N, int FMT, int SMALL, int EPI>
 __global__ void __launch_bounds__(320, SMALL ? 2 : 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmC, GemmTcArgs a) {
@@ -211,8 +217,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int col0 = nb * BLOCK_N + half * (BLOCK_N / 2) + cc * 32;
         if (col0 < a.N && (row_ok || use_tma)) {
           const uint32_t* vv = v[cc & 1];
-          uint32_t packed[16], packed_lo[16];
-          float vmax = 0.f;
+          uint32_t packed[16], packed_lo[EPI == EPI_SPLIT ? 16 : 1];
+          float vm[4] = {0.f, 0.f, 0.f, 0.f};       // four independent max chains (one chain of 32 is latency bound)
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             float f[4] = {__uint_as_float(vv[4 * j4]), __uint_as_float(vv[4 * j4 + 1]),
@@ -230,40 +236,45 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
               for (int q = 0; q < 4; ++q) f[q] = fmaxf(f[q], 0.f);
             }
-            if (a.mask != nullptr && row_ok) {
-              const uint2 mk = __ldg(reinterpret_cast<const uint2*>(a.mask + static_cast<int64_t>(row) * a.mask_ld + col0) + j4);
-              if ((mk.x & 0x7FFFu) == 0u) f[0] = 0.f;
-              if ((mk.x & 0x7FFF0000u) == 0u) f[1] = 0.f;
-              if ((mk.y & 0x7FFFu) == 0u) f[2] = 0.f;
-              if ((mk.y & 0x7FFF0000u) == 0u) f[3] = 0.f;
+            if (EPI == EPI_MASK) {
+              if (row_ok) {
+                const uint2 mk = __ldg(reinterpret_cast<const uint2*>(a.mask + static_cast<int64_t>(row) * a.mask_ld + col0) + j4);
+                if ((mk.x & 0x7FFFu) == 0u) f[0] = 0.f;
+                if ((mk.x & 0x7FFF0000u) == 0u) f[1] = 0.f;
+                if ((mk.y & 0x7FFFu) == 0u) f[2] = 0.f;
+                if ((mk.y & 0x7FFF0000u) == 0u) f[3] = 0.f;
+              }
             }
-            if (a.out_f32) {
+            if (EPI == EPI_F32) {
               if (row_ok)
                 *reinterpret_cast<float4*>(reinterpret_cast<float*>(a.C) + static_cast<int64_t>(row) * a.ldc + col0 + 4 * j4) =
                     make_float4(f[0], f[1], f[2], f[3]);
-              continue;
-            }
-            if (FMT == 0 && a.overflow != nullptr) {
+            } else {
+              if (FMT == 0 && (EPI == EPI_PLAIN || EPI == EPI_SPLIT)) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) vmax = fmaxf(vmax, fabsf(f[q]));
-            }
+                for (int q = 0; q < 4; ++q) vm[q] = fmaxf(vm[q], fabsf(f[q]));
+              }
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              if (FMT == 0) {
-                __half2 h = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
-                packed[2 * j4 + q] = *reinterpret_cast<uint32_t*>(&h);
-                if (a.c_split) {
-                  const float2 hf = __half22float2(h);
-                  __half2 l = __floats2half2_rn(f[2 * q] - hf.x, f[2 * q + 1] - hf.y);
-                  packed_lo[2 * j4 + q] = *reinterpret_cast<uint32_t*>(&l);
+              for (int q = 0; q < 2; ++q) {
+                if (FMT == 0) {
+                  __half2 h = __floats2half2_rn(f[2 * q], f[2 * q + 1]);
+                  packed[2 * j4 + q] = *reinterpret_cast<uint32_t*>(&h);
+                  if (EPI == EPI_SPLIT) {
+                    const float2 hf = __half22float2(h);
+                    __half2 l = __floats2half2_rn(f[2 * q] - hf.x, f[2 * q + 1] - hf.y);
+                    packed_lo[2 * j4 + q] = *reinterpret_cast<uint32_t*>(&l);
+                  }
+                } else {
+                  __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
+                  packed[2 * j4 + q] = *reinterpret_cast<uint32_t*>(&h);
                 }
-              } else {
-                __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * q], f[2 * q + 1]);
-                packed[2 * j4 + q] = *reinterpret_cast<uint32_t*>(&h);
               }
             }
           }
-          if (FMT == 0 && a.overflow != nullptr && row_ok && !(vmax <= 65504.f)) atomicAdd(a.overflow, 1);
+          if (FMT == 0 && (EPI == EPI_PLAIN || EPI == EPI_SPLIT)) {
+            const float vmax = fmaxf(fmaxf(vm[0], vm[1]), fmaxf(vm[2], vm[3]));
+            if (a.overflow != nullptr && row_ok && !(vmax <= 65504.f)) atomicAdd(a.overflow, 1);
+          }
           // one [32 rows x 32 cols] piece at column colx of the (possibly doubled) output
           auto store_piece = [&](const uint32_t* pk, int colx) {
             if (use_tma) {
@@ -296,9 +307,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
               st_global_v8(dst + 16, pk + 8);   // sectors, ncu r1a)
             }
           };
-          if (!a.out_f32) {
+          if (EPI != EPI_F32) {
             store_piece(packed, col0);
-            if (FMT == 0 && a.c_split) store_piece(packed_lo, col0 + a.N);
+            if (FMT == 0 && EPI == EPI_SPLIT) store_piece(packed_lo, col0 + a.N);
           }
         }
         if (cc + 1 < kChunks) tmem_ld_wait();
@@ -321,13 +332,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
 int g_num_sms = 0;
 
-template <int BLOCK_N, int FMT, int SMALL>
+template <int BLOCK_N, int FMT, int SMALL, int EPI = EPI_PLAIN>
 int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmTcArgs& a,
                     cudaStream_t st, bool pdl) {
   using Cfg = GemmCfg<BLOCK_N, SMALL>;
   static bool attr_set = false;
   if (!attr_set) {
-    NNC_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, FMT, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NNC_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<BLOCK_N, FMT, SMALL, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         Cfg::kSmemBytes));
     attr_set = true;
   }
@@ -344,7 +355,7 @@ int launch_gemm_cfg(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  NNC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<BLOCK_N, FMT, SMALL>, tmA, tmB, tmC, a));
+  NNC_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<BLOCK_N, FMT, SMALL, EPI>, tmA, tmB, tmC, a));
   return NNCONV_OK;
 }
 
@@ -431,6 +442,22 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
   a.done_cnt = pf ? pf->done_cnt : nullptr;
   a.done_ok = pf ? pf->done_ok : nullptr;
   const bool pdl = pf && pf->pdl;
+  // backward / split epilogues (never pipelined, never the small-footprint configuration)
+#define NNC_GEMM_EPI(E)                                                                                              \
+  do {                                                                                                               \
+    if (BN == 256) return bf ? launch_gemm_cfg<256, 1, 0, E>(tmA, tmB, tmC, a, st, pdl) : launch_gemm_cfg<256, 0, 0, E>(tmA, tmB, tmC, a, st, pdl); \
+    if (BN == 128) return bf ? launch_gemm_cfg<128, 1, 0, E>(tmA, tmB, tmC, a, st, pdl) : launch_gemm_cfg<128, 0, 0, E>(tmA, tmB, tmC, a, st, pdl); \
+    return bf ? launch_gemm_cfg<64, 1, 0, E>(tmA, tmB, tmC, a, st, pdl) : launch_gemm_cfg<64, 0, 0, E>(tmA, tmB, tmC, a, st, pdl); \
+  } while (0)
+  if (out_f32) { NNC_REQUIRE(!small && !c_split && mask == nullptr, NNCONV_ERR_ARG, "gemm_tc: fp32 output excludes split / mask"); NNC_GEMM_EPI(EPI_F32); }
+  if (mask != nullptr) { NNC_REQUIRE(!small && !c_split, NNCONV_ERR_ARG, "gemm_tc: mask excludes split"); NNC_GEMM_EPI(EPI_MASK); }
+  if (c_split) {
+    NNC_REQUIRE(!small, NNCONV_ERR_ARG, "gemm_tc: split output excludes the small-footprint configuration");
+    if (BN == 256) return launch_gemm_cfg<256, 0, 0, EPI_SPLIT>(tmA, tmB, tmC, a, st, pdl);
+    if (BN == 128) return launch_gemm_cfg<128, 0, 0, EPI_SPLIT>(tmA, tmB, tmC, a, st, pdl);
+    return launch_gemm_cfg<64, 0, 0, EPI_SPLIT>(tmA, tmB, tmC, a, st, pdl);
+  }
+#undef NNC_GEMM_EPI
   if (small) return bf ? launch_gemm_cfg<128, 1, 1>(tmA, tmB, tmC, a, st, pdl) : launch_gemm_cfg<128, 0, 1>(tmA, tmB, tmC, a, st, pdl);
   if (BN == 256) return bf ? launch_gemm_cfg<256, 1, 0>(tmA, tmB, tmC, a, st, pdl) : launch_gemm_cfg<256, 0, 0>(tmA, tmB, tmC, a, st, pdl);
   if (BN == 128) return bf ? launch_gemm_cfg<128, 1, 0>(tmA, tmB, tmC, a, st, pdl) : launch_gemm_cfg<128, 0, 0>(tmA, tmB, tmC, a, st, pdl);

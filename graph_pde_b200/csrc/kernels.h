@@ -79,6 +79,16 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
                     int flags_stride,
                     cudaStream_t st);
 
+// ---- loss.cu: fused loss / normaliser epilogue (ws: 2 + 2*batch floats, res: 4 floats)
+int loss_epilogue(const float* out, const float* y, const float* mean, const float* std_, float eps, int batch, int64_t n,
+                  float grad_scale, float* grad_l1, float* res, float* ws, cudaStream_t st);
+
+// ---- halo.cu: strip-partition halo exchange by peer stores + sequence flags
+int halo_push(const float* out, int relu, int64_t n_local, int C, int64_t own_lo, int64_t own_hi, float* x_next,
+              float* peer_up, int64_t up_src0, int64_t up_dst0, int64_t up_rows, float* peer_down, int64_t dn_src0,
+              int64_t dn_dst0, int64_t dn_rows, int* flag_up, int* flag_down, int seq, cudaStream_t st);
+int halo_wait(const int* flag_a, const int* flag_b, int seq, cudaStream_t st);
+
 bool tc_shapes_supported(const Weights* W);
 int tc_init();   // resolves cuTensorMapEncodeTiled, sets kernel attributes; idempotent
 

@@ -15,6 +15,7 @@ the CPU tests):
    ``StripPartition`` builds the local sub-graph with the reference's edge order, ``halo_exchange`` moves the
    boundary rows.
 """
+import ctypes
 import math
 
 import torch
@@ -121,4 +122,117 @@ def partitioned_conv_stack(conv_fn, x_local, part, edge_attr_local, depth, relu_
         x = out
         if k != depth - 1:
             x = halo_exchange(x, part, group)
+    return x[part.own_lo:part.own_hi]
+
+
+# ------------------------------------------------------------------------------------------------------
+# Halo exchange by peer stores over NVLink (csrc/halo.cu): no NCCL call and no host round trip between the T
+# applications of the conv stack.
+# ------------------------------------------------------------------------------------------------------
+def halo_ranges(part):
+    """Which of this rank's local rows go where: dict with, per direction, (src_row0, dst_row0, n_rows) in units of
+    NODES -- src in this rank's local numbering, dst in the NEIGHBOUR's local numbering.  'up' = rank-1 (its halo
+    below its strip receives my top R grid rows), 'down' = rank+1 (its halo above receives my bottom R grid rows)."""
+    s, R = part.s, part.R
+    rows = part.all_rows
+    out = {'up': None, 'down': None}
+    if part.rank > 0:
+        up_lo, up_hi = rows[part.rank - 1], rows[part.rank]
+        up_halo_lo = max(0, up_lo - R)
+        up_own_hi = (up_hi - up_halo_lo) * s                       # neighbour's local index of its first halo-below node
+        n = min(s, up_hi + R) - up_hi                              # grid rows the neighbour has below its strip
+        out['up'] = (part.own_lo, up_own_hi, n * s)
+    if part.rank < part.world - 1:
+        dn_lo = rows[part.rank + 1]
+        dn_halo_lo = max(0, dn_lo - R)
+        n = dn_lo - dn_halo_lo                                     # grid rows the neighbour has above its strip
+        out['down'] = (part.own_hi - n * s, 0, n * s)
+    return out
+
+
+class PeerHalo(object):
+    """Double-buffered node-feature buffers of one rank, mapped into the two neighbours with CUDA IPC, plus one
+    flag word per direction.  ``advance(out, k)`` turns the result of application k into the input of application
+    k+1: ReLU + copy of the owned rows + peer stores of the boundary rows + flag (one small kernel pair), then a
+    one-thread wait kernel for the neighbours' flags.  Everything is stream-ordered on the device."""
+
+    def __init__(self, part, channels, device, group=None):
+        from torch.multiprocessing.reductions import reduce_tensor
+        from . import _lib
+        self.part, self.C, self.dev, self.group = part, channels, device, group
+        self.L = _lib.lib()
+        self._lib = _lib
+        self.bufs = [torch.zeros(part.n_local, channels, device=device) for _ in range(2)]
+        self.flags = torch.zeros(2, dtype=torch.int32, device=device)        # [from_up, from_down]
+        torch.cuda.synchronize(device)
+        payload = [reduce_tensor(t) for t in self.bufs + [self.flags]]
+        gathered = [None] * part.world
+        dist.all_gather_object(gathered, payload, group=group)
+        self._keep = []
+
+        def open_(r):
+            ts = [fn(*args) for fn, args in gathered[r]]
+            self._keep.append(ts)
+            return ts
+        self.up = open_(part.rank - 1) if part.rank > 0 else None
+        self.down = open_(part.rank + 1) if part.rank < part.world - 1 else None
+        self.ranges = halo_ranges(part)
+        self.seq = 0
+        dist.barrier(group=group)
+
+    def load(self, x_local):
+        """Input of application 0 (halo rows already correct: every rank slices the same global tensor)."""
+        self.bufs[0].copy_(x_local)
+        return self.bufs[0]
+
+    def advance(self, out, k, relu=True):
+        nxt = self.bufs[(k + 1) % 2]
+        self.seq += 1
+        up, dn = self.ranges['up'], self.ranges['down']
+        p = self.part
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        vp = ctypes.c_void_p
+        peer_up = vp(self.up[(k + 1) % 2].data_ptr()) if up else vp(0)
+        peer_dn = vp(self.down[(k + 1) % 2].data_ptr()) if dn else vp(0)
+        # my rows land in the neighbour above as ITS "from_down" flag/halo, and vice versa
+        flag_up = vp(self.up[2].data_ptr() + 4) if up else vp(0)
+        flag_dn = vp(self.down[2].data_ptr()) if dn else vp(0)
+        u = up or (0, 0, 0)
+        d = dn or (0, 0, 0)
+        self._lib.check(self.L.nnconv_halo_push(vp(out.data_ptr()), 1 if relu else 0, p.n_local, self.C, p.own_lo, p.own_hi,
+                                                vp(nxt.data_ptr()), peer_up, u[0], u[1], u[2], peer_dn, d[0], d[1], d[2],
+                                                flag_up, flag_dn, self.seq, vp(st)))
+        self._lib.check(self.L.nnconv_halo_wait(vp(self.flags.data_ptr()) if up else vp(0),
+                                                vp(self.flags.data_ptr() + 4) if dn else vp(0), self.seq, vp(st)))
+        return nxt
+
+
+    def finish(self):
+        """End-of-stack handshake (flags only): returns once both neighbours have retired their last application,
+        so the next stack's pushes cannot overwrite halo rows a slower neighbour is still reading."""
+        self.seq += 1
+        up, dn = self.ranges['up'], self.ranges['down']
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        vp = ctypes.c_void_p
+        b = self.bufs[0]
+        self._lib.check(self.L.nnconv_halo_push(vp(b.data_ptr()), 0, self.part.n_local, self.C, 0, 0, vp(b.data_ptr()),
+                                                vp(self.up[0].data_ptr()) if up else vp(0), 0, 0, 0,
+                                                vp(self.down[0].data_ptr()) if dn else vp(0), 0, 0, 0,
+                                                vp(self.up[2].data_ptr() + 4) if up else vp(0),
+                                                vp(self.down[2].data_ptr()) if dn else vp(0), self.seq, vp(st)))
+        self._lib.check(self.L.nnconv_halo_wait(vp(self.flags.data_ptr()) if up else vp(0),
+                                                vp(self.flags.data_ptr() + 4) if dn else vp(0), self.seq, vp(st)))
+
+
+def partitioned_conv_stack_peer(conv_fn, x_local, part, edge_attr_local, depth, halo, relu_last=True):
+    """Same as partitioned_conv_stack with the halo moved by peer stores (PeerHalo) instead of an all-gather."""
+    x = halo.load(x_local)
+    for k in range(depth):
+        out = conv_fn(x, part.edge_index, edge_attr_local)
+        relu = relu_last or k != depth - 1
+        if k != depth - 1:
+            x = halo.advance(out, k, relu)
+        else:
+            x = torch.relu(out) if relu else out
+    halo.finish()
     return x[part.own_lo:part.own_hi]

@@ -155,6 +155,26 @@ int nnconv_backward_mlp(const nnconv_plan_t* plan, const nnconv_weights_t* w, co
                         int n_apps, const float* const* grad_out, const float* const* x, int aggr, float* const* grad_W,
                         float* const* grad_b, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- halo exchange of the node-range (strip) partition by peer stores over NVLink (no NCCL call, no host round
+ * trip between applications).  `out` [n_local, channels] is the result of one application on this rank (owned rows
+ * [own_lo, own_hi) valid); the call writes relu?(out) of the owned rows into this rank's next-application buffer
+ * x_next and the boundary rows [*_src0, +*_rows) into the neighbours' buffers (device pointers mapped with CUDA IPC,
+ * NULL at the mesh border) at rows [*_dst0, ...), then stores `seq` into the neighbours' flag words.
+ * nnconv_halo_wait makes `stream` wait until both local flag words are >= seq. */
+int nnconv_halo_push(const float* out, int relu, int64_t n_local, int channels, int64_t own_lo, int64_t own_hi,
+                     float* x_next, float* peer_up, int64_t up_src0, int64_t up_dst0, int64_t up_rows, float* peer_down,
+                     int64_t dn_src0, int64_t dn_dst0, int64_t dn_rows, int* flag_up, int* flag_down, int seq,
+                     void* stream);
+int nnconv_halo_wait(const int* flag_from_up, const int* flag_from_down, int seq, void* stream);
+
+/* ---- fused loss / normaliser epilogue after fc2 (UAI1_full_resolution.py:262-268, utilities.py:87-99,184-199):
+ * out, y [batch, n] fp32; mean / std [n] of the UnitGaussianNormalizer (NULL = identity decode).  One pass writes
+ * results[0] = mse_loss(out, y), [1] = ||out - y||_1, [2] = sum_b rel-L2 of the DECODED fields, [3] = their mean,
+ * and, if grad_l1 != NULL, grad_l1 = grad_scale * sign(out - y) (the backward of results[1]).  ws: 2 + 2*batch floats.
+ * Nothing is copied to the host. */
+int nnconv_loss_epilogue(const float* out, const float* y, const float* mean, const float* std_, float eps, int batch,
+                         int64_t n, float grad_scale, float* grad_l1, float* results, float* ws, void* stream);
+
 /* ---- measurement hook (bench.py): while enabled, every kernel launch is bracketed by CUDA events on its
  * stream; profile_end synchronises the device and returns summed milliseconds / launch counts per kernel
  * class: 0 first MLP layer, 1 hidden-layer GEMM, 2 per-node prologue, 3 per-source Y GEMM (unfused path),

@@ -118,3 +118,25 @@ def test_batch_sharding_and_gradient_allreduce():
         ea = graphs.ball_edge_attr(grid, ei, th)
         lin(O.kernelnn_conv_stack(x, ei, ea, ws, bs, root, bias, 2)).sum().backward()
     np.testing.assert_allclose(res[0][1], lin.weight.grad.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_peer_halo_row_ranges_reproduce_the_all_gather_exchange():
+    """halo_ranges (what PeerHalo pushes into the neighbours' buffers on the GPU) moves exactly the rows
+    halo_exchange moves: simulate the pushes with plain copies between per-rank tensors."""
+    world, C = 4, 3
+    torch.manual_seed(1)
+    xg = torch.randn(S * S, C)
+    parts = [partition.StripPartition(S, R_, r, world) for r in range(world)]
+    local = [torch.zeros(p.n_local, C) for p in parts]
+    for p, x in zip(parts, local):
+        x[p.own_lo:p.own_hi] = xg[p.row_lo * S:p.row_hi * S]          # only owned rows are known after an application
+    for p, x in zip(parts, local):
+        rg = partition.halo_ranges(p)
+        if rg['up'] is not None:
+            src, dst, n = rg['up']
+            local[p.rank - 1][dst:dst + n] = x[src:src + n]
+        if rg['down'] is not None:
+            src, dst, n = rg['down']
+            local[p.rank + 1][dst:dst + n] = x[src:src + n]
+    for p, x in zip(parts, local):
+        assert torch.equal(x, p.local_slice(xg)), p.rank

@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 from tests.helpers import GOLDEN, TOL, cfg1_weights, ei64, rel_err, t
 
@@ -119,3 +120,32 @@ def test_cuda_graph_replay_of_kernelnn_and_vcycle():
     dv.edge_index_up_range = torch.from_numpy(g4['range_up']).to(DEV)
     gv = GraphedForward(vm, dv)
     assert rel_err(gv.replay(), t(g4['neurips1/out'])) < TOL['f16']
+
+
+def test_fused_loss_epilogue_matches_reference_formulas():
+    """f4: one pass for mse_loss, the differentiated L1 norm and LpLoss.rel of the decoded fields
+    (UAI1_full_resolution.py:262-268; utilities.py:87-99, 184-199) -- against the formulas written with torch ops."""
+    from graph_pde_b200.losses import fused_losses
+    dev = torch.device('cuda:0')
+    g = torch.Generator().manual_seed(0)
+    B, n = 4, 3000
+    out = torch.randn(B * n, 1, generator=g).to(dev).requires_grad_(True)
+    y = torch.randn(B * n, generator=g).to(dev)
+
+    class Norm(object):                      # UnitGaussianNormalizer's fields (utilities.py:70-78)
+        mean = torch.randn(n, generator=g)
+        std = torch.rand(n, generator=g) + 0.5
+        eps = 1e-5
+    loss, st = fused_losses(out, y, batch_size=B, normalizer=Norm)
+    loss.backward()
+    o2 = out.detach().clone().requires_grad_(True)
+    ref_l1 = torch.norm(o2.view(-1) - y.view(-1), 1)
+    ref_l1.backward()
+    mean, std = Norm.mean.to(dev), Norm.std.to(dev)
+    dec = lambda v: v.view(B, -1) * (std + Norm.eps) + mean      # noqa: E731
+    diff = torch.norm(dec(o2.detach()) - dec(y), 2, 1)
+    rel = diff / torch.norm(dec(y), 2, 1)
+    ref = torch.stack([F.mse_loss(o2.detach().view(-1, 1), y.view(-1, 1)), ref_l1.detach(), rel.sum(), rel.mean()])
+    assert float((st - ref).abs().max() / ref.abs().max()) < 1e-5
+    assert abs(float(loss) - float(ref_l1)) / float(ref_l1) < 1e-5
+    assert torch.equal(out.grad, o2.grad)
