@@ -28,6 +28,7 @@ SYMBOLS = [
     'nnconv_backward_tc_supported', 'nnconv_backward_apply_sizes', 'nnconv_backward_apply',
     'nnconv_backward_mlp_sizes', 'nnconv_backward_mlp', 'nnconv_gemm_tn_16b', 'nnconv_gemm_16b_ex',
     'nnconv_halo_push', 'nnconv_halo_wait', 'nnconv_loss_epilogue',
+    'nnconv_ball_count', 'nnconv_ball_fill',
 ]
 
 
@@ -99,6 +100,9 @@ def lib():
     L.nnconv_halo_push.argtypes = [c_vp, c_int, c_i64, c_int, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64,
                                    c_i64, c_i64, c_vp, c_vp, c_int, c_vp]
     L.nnconv_halo_wait.argtypes = [c_vp, c_vp, c_int, c_vp]
+    L.nnconv_ball_count.argtypes = [c_vp, c_i64, c_vp, c_i64, ctypes.c_double, c_vp, c_vp]
+    L.nnconv_ball_fill.argtypes = [c_vp, c_i64, c_vp, c_i64, ctypes.c_double, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp,
+                                   c_vp, c_vp]
     L.nnconv_loss_epilogue.argtypes = [c_vp, c_vp, c_vp, c_vp, ctypes.c_float, c_int, c_i64, ctypes.c_float, c_vp, c_vp,
                                        c_vp, c_vp]
     L.nnconv_gemm_tn_16b.argtypes = [c_int, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_int, c_vp, c_i64, ctypes.c_float,

@@ -724,6 +724,20 @@ int nnconv_loss_epilogue(const float* out, const float* y, const float* mean, co
   return loss_epilogue(out, y, mean, std_, eps, batch, n, grad_scale, grad_l1, results, ws, static_cast<cudaStream_t>(stream));
 }
 
+int nnconv_ball_count(const double* pa, int64_t na, const double* pb, int64_t nb, double radius, int* counts, void* stream) {
+  NNC_REQUIRE(pa && pb && counts && na >= 0 && nb >= 0, NNCONV_ERR_ARG, "ball_count: bad arguments");
+  return ball_count(pa, na, pb, nb, radius, counts, static_cast<cudaStream_t>(stream));
+}
+
+int nnconv_ball_fill(const double* pa, int64_t na, const double* pb, int64_t nb, double radius, const int64_t* offsets,
+                     int64_t src_base, int64_t dst_base, int64_t* row0, int64_t* row1, const double* theta_a,
+                     const double* theta_b, float* edge_attr, void* stream) {
+  NNC_REQUIRE(pa && pb && offsets && row0 && row1 && (theta_a == nullptr) == (theta_b == nullptr), NNCONV_ERR_ARG,
+              "ball_fill: bad arguments");
+  return ball_fill(pa, na, pb, nb, radius, offsets, src_base, dst_base, row0, row1, theta_a, theta_b, edge_attr,
+                   static_cast<cudaStream_t>(stream));
+}
+
 int nnconv_profile_begin(void) {
   for (auto& r : nnc::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   nnc::g_prof.clear();

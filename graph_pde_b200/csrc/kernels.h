@@ -79,6 +79,12 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
                     int flags_stride,
                     cudaStream_t st);
 
+// ---- graph_build.cu: ball graph (count / fill) on the device
+int ball_count(const double* pa, int64_t na, const double* pb, int64_t nb, double radius, int* counts, cudaStream_t st);
+int ball_fill(const double* pa, int64_t na, const double* pb, int64_t nb, double radius, const int64_t* offsets,
+              int64_t src_base, int64_t dst_base, int64_t* row0, int64_t* row1, const double* theta_a,
+              const double* theta_b, float* attr, cudaStream_t st);
+
 // ---- loss.cu: fused loss / normaliser epilogue (ws: 2 + 2*batch floats, res: 4 floats)
 int loss_epilogue(const float* out, const float* y, const float* mean, const float* std_, float eps, int batch, int64_t n,
                   float grad_scale, float* grad_l1, float* res, float* ws, cudaStream_t st);

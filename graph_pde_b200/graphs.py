@@ -80,9 +80,49 @@ def darcy_sample(s, r, device='cpu', seed=0, edge_index=None, ties_in=True):
 # Multi-level (MGKN) graphs: RandomMultiMeshGenerator restated (multipole-graph-neural-operator/
 # utilities.py:546-712) with torch ops on any device.
 # ------------------------------------------------------------------------------------------------------
+def ball_pairs_device(pa, pb, radius, src_base=0, dst_base=0, theta_a=None, theta_b=None, with_attr=False):
+    """np.vstack(np.where(pairwise_distances(pa, pb) <= radius)) on the GPU without the N x N matrix: the
+    hand-written count / fill kernels of csrc/graph_build.cu (one thread per source point walks the destination
+    points in ascending order, so the row-major edge order needs no sort).  pa [na,2], pb [nb,2] CUDA tensors.
+    Returns edge_index [2,E] int64 (ids offset by src_base / dst_base) and, with_attr, edge_attr [E, 4 | 6] fp32 =
+    [pos_src, pos_dst (, theta_src, theta_dst)] (utilities.py:269-285 / multipole utilities.py:672-706)."""
+    import ctypes
+
+    from . import _lib
+    L = _lib.lib()
+    dev = pa.device
+    pa64 = pa.detach().to(torch.float64).contiguous()
+    pb64 = pb.detach().to(torch.float64).contiguous()
+    na, nb = pa64.size(0), pb64.size(0)
+    vp = ctypes.c_void_p
+    with torch.cuda.device(dev):
+        st = vp(torch.cuda.current_stream(dev).cuda_stream)
+        counts = torch.empty(max(na, 1), dtype=torch.int32, device=dev)
+        _lib.check(L.nnconv_ball_count(vp(pa64.data_ptr()), na, vp(pb64.data_ptr()), nb, float(radius),
+                                       vp(counts.data_ptr()), st))
+        incl = torch.cumsum(counts[:na].to(torch.int64), 0)
+        e = int(incl[-1].item()) if na > 0 else 0            # one host read per graph (the edge count sizes the output)
+        offsets = (incl - counts[:na]).contiguous()
+        ei = torch.empty(2, e, dtype=torch.int64, device=dev)
+        ta = theta_a.detach().to(torch.float64).contiguous() if theta_a is not None else None
+        tb = theta_b.detach().to(torch.float64).contiguous() if theta_b is not None else None
+        attr = torch.empty(e, 6 if ta is not None else 4, dtype=torch.float32, device=dev) if with_attr else None
+        if e > 0:
+            _lib.check(L.nnconv_ball_fill(vp(pa64.data_ptr()), na, vp(pb64.data_ptr()), nb, float(radius),
+                                          vp(offsets.data_ptr()), int(src_base), int(dst_base), vp(ei[0].data_ptr()),
+                                          vp(ei[1].data_ptr()), vp(ta.data_ptr()) if ta is not None else vp(0),
+                                          vp(tb.data_ptr()) if tb is not None else vp(0),
+                                          vp(attr.data_ptr()) if attr is not None else vp(0), st))
+    return (ei, attr) if with_attr else ei
+
+
 def _ball_pairs(pa, pb, radius):
     """np.vstack(np.where(pairwise_distances(pa, pb) <= radius)): row-major order = source-major, dst ascending.
-    Float64 distances; lattice ties with `radius` are rounding-dependent in the reference too."""
+    Float64 distances; lattice ties with `radius` are rounding-dependent in the reference too.
+    CUDA tensors go through the device kernels (no N x N matrix); the dense torch.cdist form is the CPU path used
+    by the host-side tests."""
+    if pa.is_cuda:
+        return ball_pairs_device(pa, pb, radius)
     d = torch.cdist(pa.double(), pb.double())
     idx = torch.nonzero(d <= radius, as_tuple=False)
     return idx.t().contiguous()

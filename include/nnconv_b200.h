@@ -167,6 +167,18 @@ int nnconv_halo_push(const float* out, int relu, int64_t n_local, int channels, 
                      void* stream);
 int nnconv_halo_wait(const int* flag_from_up, const int* flag_from_down, int seq, void* stream);
 
+/* ---- ball-graph construction on the device (replaces np.where(pairwise_distances(pa, pb) <= r), utilities.py:250-255
+ * and multipole utilities.py:602-643, plus the attribute gather :269-285 / :672-706), two passes:
+ *   nnconv_ball_count: counts[i] = #{j : |pa_i - pb_j| <= radius}        (pa [na,2], pb [nb,2] float64, device)
+ *   (the caller turns counts into exclusive offsets)
+ *   nnconv_ball_fill:  edges of source i at [offsets[i], ...) in ascending j: row0 = src_base + i, row1 = dst_base + j,
+ *                      edge_attr (nullable) = [pa_i, pb_j] (+ [theta_a_i, theta_b_j] when the thetas are given), fp32.
+ * Same float64 distance formula as sklearn (see csrc/graph_build.cu); edge order = np.where's row-major order. */
+int nnconv_ball_count(const double* pa, int64_t na, const double* pb, int64_t nb, double radius, int* counts, void* stream);
+int nnconv_ball_fill(const double* pa, int64_t na, const double* pb, int64_t nb, double radius, const int64_t* offsets,
+                     int64_t src_base, int64_t dst_base, int64_t* row0, int64_t* row1, const double* theta_a,
+                     const double* theta_b, float* edge_attr, void* stream);
+
 /* ---- fused loss / normaliser epilogue after fc2 (UAI1_full_resolution.py:262-268, utilities.py:87-99,184-199):
  * out, y [batch, n] fp32; mean / std [n] of the UnitGaussianNormalizer (NULL = identity decode).  One pass writes
  * results[0] = mse_loss(out, y), [1] = ||out - y||_1, [2] = sum_b rel-L2 of the DECODED fields, [3] = their mean,
