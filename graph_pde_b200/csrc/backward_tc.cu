@@ -655,7 +655,6 @@ bool backward_tc_supported(const Weights* W) {
   if (W->cout != 64 || W->cin > 64 || W->n_layers < 2 || W->W1aug == nullptr) return false;
   if (W->W3q == nullptr || W->W3t == nullptr) return false;
   if ((W->Kp + 127) / 128 * 64 > 512) return false;                  // k_dy accumulators
-  if (W->Kp > 256 && W->Kp % 256 != 0) return false;                  // k_dh k blocks
   for (int l = 2; l <= W->n_layers - 1; ++l)
     if (W->WhT[l] == nullptr) return false;
   return true;
@@ -908,7 +907,7 @@ int backward_mlp_tc(const Plan* P, const Weights* W, const float* edge_attr, con
   const int* htp = P->h_tile_ptr;
   const size_t avail = ws_bytes - L.fixed - (1 << 16);
   const int64_t e_pad = round_up64(P->E, 128);
-  const int BN = Kp >= 256 ? 256 : Kp;
+  const int BN = Kp % 256 == 0 ? 256 : Kp % 128 == 0 ? 128 : 64;   // k block of k_dh (Kp is a multiple of 64)
   int maxkp = 0;
   for (int l = 1; l <= nl - 1; ++l) maxkp = W->kp[l] > maxkp ? W->kp[l] : maxkp;
   static bool attr_set = false;

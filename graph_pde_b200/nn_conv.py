@@ -235,6 +235,7 @@ class _EdgeFeaturesFn(torch.autograd.Function):
         grads = ctx.module._backward_mlp_impl(state)
         state.consumed = True
         state.apps = []
+        state.h = state.ea32 = None          # the 2 KB/edge features are no longer pinned by this (finished) graph
         return (None, None) + tuple(grads)
 
 

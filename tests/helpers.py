@@ -103,19 +103,24 @@ def ste_round(t, prec):
     return t + (t.to(dt).to(t.dtype) - t).detach()
 
 
-def emulated_nnconv_forward(x, edge_index, edge_attr, weights, biases, root, bias, aggr, prec):
+def emulated_nnconv_forward(x, edge_index, edge_attr, weights, biases, root, bias, aggr, prec, edge_chunk=None):
     n, cin = x.shape
     cout = weights[-1].size(0) // cin
-    h = edge_attr
-    for l in range(len(weights) - 1):
-        w = weights[l] if l == 0 else ste_round(weights[l], prec)     # layer 1 runs fp32-grade (hi/lo split)
-        h = ste_round(torch.relu(h @ w.t() + biases[l]), prec)       # activations are stored in 16 bit
-    k = (h @ weights[-1].t() + biases[-1]).view(-1, cin, cout)
-    msg = torch.matmul(x.index_select(0, edge_index[0]).unsqueeze(1), k).squeeze(1)
-    out = torch.zeros(n, cout, dtype=x.dtype, device=x.device).index_add_(0, edge_index[1], msg)
+    e_total = edge_index.size(1)
+    step = e_total if not edge_chunk else edge_chunk
+    out = torch.zeros(n, cout, dtype=x.dtype, device=x.device)
+    wq = [weights[0]] + [ste_round(w, prec) for w in weights[1:-1]]      # layer 1 runs fp32-grade (hi/lo split)
+    for s0 in range(0, max(e_total, 1), max(step, 1)):
+        sl = slice(s0, min(s0 + step, e_total))
+        h = edge_attr[sl]
+        for l in range(len(weights) - 1):
+            h = ste_round(torch.relu(h @ wq[l].t() + biases[l]), prec)   # activations are stored in 16 bit
+        k = (h @ weights[-1].t() + biases[-1]).view(-1, cin, cout)
+        msg = torch.matmul(x.index_select(0, edge_index[0, sl]).unsqueeze(1), k).squeeze(1)
+        out = out.index_add(0, edge_index[1, sl], msg)
     if aggr == 'mean':
         cnt = torch.zeros(n, dtype=x.dtype, device=x.device).index_add_(
-            0, edge_index[1], torch.ones(edge_index.size(1), dtype=x.dtype, device=x.device))
+            0, edge_index[1], torch.ones(e_total, dtype=x.dtype, device=x.device))
         out = out / cnt.clamp(min=1).unsqueeze(-1)
     if root is not None:
         out = out + x @ root

@@ -80,7 +80,7 @@ def _graph(gen, N, E, hub=False):
     ([6, 64, 64, 64 * 64], 64, 'mean', True, True, 'f16'),
     ([6, 64, 64, 64 * 64], 64, 'add', True, True, 'bf16'),
     ([6, 128, 32 * 64], 32, 'mean', False, False, 'f16'),            # 2-layer MLP (MGKN down/up), in < out
-    ([4, 256, 320, 64 * 64], 64, 'mean', True, False, 'f16'),        # k_in = 4, Kp = 320 (odd number of 64-chunks)
+    ([4, 256, 320, 64 * 64], 64, 'mean', True, False, 'f16'),        # k_in = 4, Kp = 320: odd number of 64-chunks, k block 64
     ([6, 16, 32, 24, 64 * 64], 64, 'add', False, True, 'f16'),       # 4-layer MLP, widths padded to 64
 ])
 def test_tc_backward_matches_autograd_through_oracle(layers, cin, aggr, rw, bs, prec):
@@ -189,8 +189,10 @@ def test_kernelnn_training_step_tc(dev=DEV):
 
 
 def test_tc_backward_config2_size():
-    """BASELINE config-2 size graph (85x85, r=0.10, E = 1,466,497), w=64, ker_width=256 (so that autograd through
-    the reference-equivalent fp32 torch ops fits on the GPU: 12 KB saved per edge), T=2 shared applications."""
+    """BASELINE config-2 size graph (85x85, r=0.10, E = 1,466,497), w=64, ker_width=256, T=2 shared applications:
+    every source has two edge tiles, every CTA of k_dy / k_dh walks many sources / tiles.  Reference: autograd through
+    the mask-consistent forward (fp32 torch ops on the GPU, TF32 off, edge-chunked), node-level ReLUs evaluated at the
+    CUDA path's own conv outputs."""
     from graph_pde_b200 import graphs
     from graph_pde_b200.nn_conv import NNConv_old
     s, r, w, kw, T = 85, 0.10, 64, 256, 2
@@ -201,36 +203,39 @@ def test_tc_backward_config2_size():
     torch.manual_seed(1)
     x0 = torch.randn(s * s, w, device=dev)
     gout = torch.randn(s * s, w, device=dev)
-    # reference: autograd through the oracle ops on CUDA (fp32, TF32 off), edges in one shot per application
-    old = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = False
-    try:
-        leaves = [t.to(dev).clone().requires_grad_(True) for t in [x0.cpu()] + ws + bs + [root, bias]]
-        xr, wr, br, rr, bbr = leaves[0], leaves[1:4], leaves[4:7], leaves[7], leaves[8]
-        h = xr
-        for _ in range(T):
-            h = torch.relu(O.nnconv_forward(h, ei, ea, wr, br, rr, bbr, 'mean', w, w, edge_chunk=1 << 18))
-        (h * gout).sum().backward()
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = old
-    ref = {'x': xr.grad, 'root': rr.grad, 'bias': bbr.grad}
-    for i in range(3):
-        ref['W%d' % i], ref['b%d' % i] = wr[i].grad, br[i].grad
-    ref = {k: v.detach().cpu() for k, v in ref.items()}
-    del leaves, h
-    torch.cuda.empty_cache()
     conv = make_conv(NNConv_old, ws, bs, root, bias, 'mean', w, w, 'f16', dev)
+    conv_outs = []
+    hook = conv.register_forward_hook(lambda m, i, o: conv_outs.append(o.detach()))
     xd = x0.clone().requires_grad_(True)
     h = xd
     for _ in range(T):
         h = torch.relu(conv(h, ei, ea))
     (h * gout).sum().backward()
+    hook.remove()
     lin_d = [m for m in conv.nn.layers if isinstance(m, torch.nn.Linear)]
     got = {'x': xd.grad, 'root': conv.root.grad, 'bias': conv.bias.grad}
     for i, l in enumerate(lin_d):
         got['W%d' % i], got['b%d' % i] = l.weight.grad, l.bias.grad
-    # exact fp32 reference: the loose bound (ReLU masks of the 16-bit forward differ on ~1e-4 of the units)
+    got = {k: v.detach().cpu() for k, v in got.items()}
+    conv._h_cache.clear()
+    conv._tstate = None
+    torch.cuda.empty_cache()
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        leaves = [t.to(dev).clone().requires_grad_(True) for t in [x0.cpu()] + ws + bs + [root, bias]]
+        xr, wr, br, rr, bbr = leaves[0], leaves[1:4], leaves[4:7], leaves[7], leaves[8]
+        hr = xr
+        for k in range(T):
+            o = emulated_nnconv_forward(hr, ei, ea, wr, br, rr, bbr, 'mean', 'f16', edge_chunk=1 << 17)
+            hr = torch.relu(o + (conv_outs[k] - o).detach())
+        (hr * gout).sum().backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    ref = {'x': xr.grad, 'root': rr.grad, 'bias': bbr.grad}
+    for i in range(3):
+        ref['W%d' % i], ref['b%d' % i] = wr[i].grad, br[i].grad
     errs = {k: _relerr(got[k], ref[k]) for k in ref}
-    bad = {k: v for k, v in errs.items() if not v < GTOL_EXACT}
+    print('config-2-size gradient errors vs mask-consistent fp32 autograd:', errs)
+    bad = {k: v for k, v in errs.items() if not v < 5e-3}
     assert not bad, (bad, errs)
-    print('config-2-size gradient errors vs exact fp32 autograd:', errs)

@@ -167,3 +167,25 @@ def test_dropin_modules_resolve_like_the_reference_imports(monkeypatch):
     assert batch.x.shape == (5, 2) and batch.edge_index.tolist() == [[0, 1, 3], [1, 2, 4]]
     for m in ('nn_conv', 'torch_geometric', 'torch_geometric.nn', 'torch_geometric.data'):
         sys.modules.pop(m, None)
+
+
+def test_device_resident_loader_shares_the_mesh_and_caches_block_diagonal_index():
+    """f3: DataLoader(device=...) moves the dataset once, keeps the shared edge_index shared, collates on that device
+    and reuses ONE block-diagonal edge_index per batch size (so the conv's plan cache hits every step)."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'dropin', 'torch_geometric', 'data',
+                        '__init__.py')
+    spec = importlib.util.spec_from_file_location('dropin_pyg_data', path)
+    D = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(D)
+    ei = torch.tensor([[0, 1, 2], [1, 2, 0]])
+    data = [D.Data(x=torch.randn(3, 2), y=torch.randn(3), edge_index=ei, edge_attr=torch.randn(3, 4)) for _ in range(6)]
+    loader = D.DataLoader(data, batch_size=2, shuffle=True, device='cpu')
+    assert all(it.edge_index is loader.dataset[0].edge_index for it in loader.dataset)      # still one mesh tensor
+    batches = list(loader)
+    assert len(batches) == 3
+    assert all(b.edge_index is batches[0].edge_index for b in batches)                      # cached block diagonal
+    assert batches[0].edge_index.tolist() == [[0, 1, 2, 3, 4, 5], [1, 2, 0, 4, 5, 3]]
+    assert batches[0].x.shape == (6, 2) and batches[0].batch.tolist() == [0, 0, 0, 1, 1, 1]
+    single = next(iter(D.DataLoader(data, batch_size=1)))
+    assert single is not data[0] and single.x is data[0].x                                   # shallow copy of the item
