@@ -232,6 +232,123 @@ def rel_err(out, ref):
     return float((out.double() - ref.double()).abs().max() / ref.double().abs().max().clamp(min=1e-30))
 
 
+def _time_ms(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def other_configs(dev, precision):
+    """The BASELINE.json configs that are not the metric configuration, each as value + parity (rank 0, one GPU):
+    config 2 (GKN 85^2), config 4 (MGKN V-cycle, neurips1_MGKN.py case 0 on the 241^2 grid), config 5 (orthogonal MGKN,
+    Burgers 1-D, s=8192, 5 levels).  Parity = whole-model output against the oracle port run with fp32 torch ops on
+    the same GPU; `ref_ms` is that path's time (the 'reference single-GPU path')."""
+    from graph_pde_b200 import GraphedForward, graphs, nn_conv
+    from graph_pde_b200.models import MGKN, KernelInduced, KernelNN
+    from oracle import nnconv_oracle as O
+    out = {}
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            # ---- config 2
+            cfg = WORKLOADS['darcy85']
+            s, r, w, kw, T = cfg['s'], cfg['r'], cfg['width'], cfg['ker_width'], cfg['depth']
+            torch.manual_seed(0)
+            m = KernelNN(w, kw, T, 6, in_width=6, precision=precision).to(dev).eval()
+            x6, ei, ea = graphs.darcy_sample(s, r, dev, seed=5)
+            x0 = m.fc1(x6)
+
+            def step2():
+                m.conv1._h_cache.clear()
+                return m.conv_stack(x0, ei, ea)
+            ms = _time_ms(step2, 10)
+            ref = oracle_stack_cuda(cfg, m, x0, ei, ea)
+            out['darcy85'] = dict(config='GKN Darcy-2D 85x85 r=0.10 width=64 ker_width=1024 T=6 (BASELINE configs[1])',
+                                  edges=int(ei.size(1)), value=ei.size(1) * T / (ms * 1e-3), unit='edge-apps/s', ms_per_step=ms,
+                                  parity=dict(max_rel_err=rel_err(step2(), ref), tol=TOL.get(precision)),
+                                  hbm_stream_frac=ei.size(1) * T * (2 * kw + 4) / (ms * 1e-3) / 1e9 / peaks()['hbm_gbs'])
+            del m
+            # ---- config 4
+            torch.manual_seed(0)
+            s4, mm = 241, [2400, 1600, 400, 100, 25]
+            ri = [0.5 / 8 * 1.41, 0.5 / 8, 0.5 / 4, 0.5 / 2, 0.5]
+            rx = [0.5 / 8 * 1.1, 0.5 / 8 * 1.41, 0.5 / 4 * 1.41, 0.5 / 2 * 1.41]
+            t0 = time.perf_counter()
+            g = graphs.multi_level_ball_graph(s4, mm, ri, rx, theta=torch.randn(s4 * s4), device=dev)
+            torch.cuda.synchronize()
+            build_ms = (time.perf_counter() - t0) * 1e3
+            depth = 4
+            mk = KernelInduced(width=64, ker_width=256, depth=depth, ker_in=6, points=mm, level=len(mm), in_width=6,
+                               precision=precision).to(dev).eval()
+            g.x = torch.randn(sum(mm), 6, device=dev)
+            ea4 = depth * (g.edge_index_mid.size(1) + g.edge_index_down.size(1) + g.edge_index_up.size(1))
+            o4 = mk(g)
+            ms_e = _time_ms(lambda: mk(g), 20)
+            l0 = nn_conv.stats['launches']
+            mk(g)
+            launches = nn_conv.stats['launches'] - l0
+            ms_g = None
+            try:
+                gf = GraphedForward(mk, g)
+                ms_g = _time_ms(gf.replay, 50)
+            except Exception:      # capture is an optimisation; the eager number stands on its own
+                pass
+            p = {k: v.detach() for k, v in mk.state_dict().items()}
+            data = dict(edge_index_down=g.edge_index_down, edge_index_mid=g.edge_index_mid, edge_index_up=g.edge_index_up,
+                        edge_attr_down=g.edge_attr_down, edge_attr_mid=g.edge_attr_mid, edge_attr_up=g.edge_attr_up,
+                        range_down=g.edge_index_down_range.tolist(), range_mid=g.edge_index_range.tolist(),
+                        range_up=g.edge_index_up_range.tolist())
+            ref4 = O.mgkn_vcycle_forward(g.x, data, p, depth, len(mm), mm, variant='neurips1')
+            ms_r = _time_ms(lambda: O.mgkn_vcycle_forward(g.x, data, p, depth, len(mm), mm, variant='neurips1'), 3, 1)
+            out['mgkn241'] = dict(config='MGKN V-cycle (neurips1_MGKN.py case 0): 5 levels m=%s on the 241^2 grid, width 64, '
+                                         'ker_width 256, depth 4 (BASELINE configs[3])' % mm,
+                                  edge_apps_per_forward=int(ea4), value=ea4 / (ms_e * 1e-3), unit='edge-apps/s',
+                                  ms_per_forward=ms_e, ms_per_forward_cuda_graph=ms_g, nnconv_launches_per_forward=int(launches),
+                                  graph_build_ms=build_ms, ref_ms=ms_r,
+                                  parity=dict(max_rel_err=rel_err(o4, ref4), tol=TOL.get(precision)))
+            del mk, g
+            # ---- config 5
+            torch.manual_seed(0)
+            s5, levels, width = 8192, 5, 64
+            X, eis, eas = graphs.multi_pole_grid1d(torch.randn(s5), s5, is_periodic=True, levels=levels, device=dev)
+            m5 = MGKN(width=width, ker_width=1024, depth=depth, ker_in=4, in_width=2, s=s5, precision=precision).to(dev).eval()
+            data5 = (X, None, eis, eas)
+            ea5 = depth * sum(e.size(1) for e in eis)
+            o5 = m5(data5)
+            ms_e = _time_ms(lambda: m5(data5), 20)
+            ms_g = None
+            try:
+                gf = GraphedForward(m5, data5)
+                ms_g = _time_ms(gf.replay, 50)
+            except Exception:
+                pass
+            p5 = {k: v.detach() for k, v in m5.state_dict().items()}
+            ref5 = O.mgkn_orthogonal_forward(X[0], eis, eas, p5, depth, width, s5)
+            ms_r = _time_ms(lambda: O.mgkn_orthogonal_forward(X[0], eis, eas, p5, depth, width, s5), 3, 1)
+            kbytes = sum(e.size(1) for e in eis) * depth * width * width * 2
+            out['burgers8192'] = dict(config='orthogonal MGKN (MGKN_orthogonal_burgers1d.py), s=8192, 5 levels, width 64, '
+                                             'ker_width 1024, depth 4 (BASELINE configs[4]); 2-4 out-edges per node -> per-edge '
+                                             'kernel matrices (formulation B)',
+                                      edge_sets=[int(e.size(1)) for e in eis], edge_apps_per_forward=int(ea5),
+                                      value=ea5 / (ms_e * 1e-3), unit='edge-apps/s', ms_per_forward=ms_e,
+                                      ms_per_forward_cuda_graph=ms_g, ref_ms=ms_r,
+                                      kmat_stream_gb_per_forward=kbytes / 1e9,
+                                      hbm_stream_frac=kbytes / ((ms_g or ms_e) * 1e-3) / 1e9 / peaks()['hbm_gbs'],
+                                      parity=dict(max_rel_err=rel_err(o5, ref5), tol=TOL.get(precision)))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+        torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -243,6 +360,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-parity', action='store_true', help='skip the full-graph parity check and the fp32-grade line')
     ap.add_argument('--no-train', action='store_true', help='skip the training-step measurement')
+    ap.add_argument('--no-other-configs', action='store_true', help='skip BASELINE configs 2, 4, 5')
     ap.add_argument('--no-strip', action='store_true', help='skip the single-mesh strip-partition measurement (N > 1)')
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
@@ -529,6 +647,16 @@ def main():
         torch.cuda.empty_cache()
     barrier()
 
+    configs = None
+    if rank == 0 and not args.no_other_configs and args.precision in ('f16', 'bf16'):
+        model.conv1._h_cache.clear()
+        torch.cuda.empty_cache()
+        try:
+            configs = other_configs(dev, args.precision)
+        except Exception as exc:           # never lose the headline line to a secondary measurement
+            configs = dict(error='%s: %s' % (type(exc).__name__, str(exc)[:300]))
+    barrier()
+
     if rank == 0:
         pk = peaks()
         Kp = ((kw + 63) // 64) * 64
@@ -573,7 +701,7 @@ def main():
                                               'edge-app of the reference formulation; the hoisted/reassociated '
                                               'kernels execute ~40x fewer FLOPs, so formA_tensor_frac may exceed 1'
                                               % (f_alg, b_alg)),
-                    edges=E, nodes=N, parity=parity, fp32_grade=fp32_grade, train=train, strip=strip)
+                    edges=E, nodes=N, parity=parity, fp32_grade=fp32_grade, train=train, strip=strip, configs=configs)
         if not args.no_cpu_baseline:
             line['gpu_reference_port'] = gpu_reference_rate(cfg, dev)
             rate, cores, kind, desc, _ = cpu_reference_rate(cfg, steps=2)

@@ -29,6 +29,7 @@ SYMBOLS = [
     'nnconv_backward_mlp_sizes', 'nnconv_backward_mlp', 'nnconv_gemm_tn_16b', 'nnconv_gemm_16b_ex',
     'nnconv_halo_push', 'nnconv_halo_wait', 'nnconv_loss_epilogue',
     'nnconv_ball_count', 'nnconv_ball_fill',
+    'nnconv_edge_kernels_sizes', 'nnconv_edge_kernels', 'nnconv_apply_edge',
 ]
 
 
@@ -100,6 +101,9 @@ def lib():
     L.nnconv_halo_push.argtypes = [c_vp, c_int, c_i64, c_int, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64,
                                    c_i64, c_i64, c_vp, c_vp, c_int, c_vp]
     L.nnconv_halo_wait.argtypes = [c_vp, c_vp, c_int, c_vp]
+    L.nnconv_edge_kernels_sizes.argtypes = [c_vp, c_vp, P(c_sz)]
+    L.nnconv_edge_kernels.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp]
+    L.nnconv_apply_edge.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]
     L.nnconv_ball_count.argtypes = [c_vp, c_i64, c_vp, c_i64, ctypes.c_double, c_vp, c_vp]
     L.nnconv_ball_fill.argtypes = [c_vp, c_i64, c_vp, c_i64, ctypes.c_double, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp,
                                    c_vp, c_vp]

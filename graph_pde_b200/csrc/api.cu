@@ -48,7 +48,7 @@ static size_t esize_of(int prec) { return prec == PREC_FP32 ? 4 : 2; }
 // ------------------------------------------------------------------------------------------------
 struct WeightsLayout {
   size_t off_W1, off_b1, off_W1aug, off_Wh[kMaxLayers], off_bh[kMaxLayers], off_W3p, off_B3, bytes;
-  size_t off_W3q, off_W3t, off_WhT[kMaxLayers];
+  size_t off_W3q, off_W3t, off_WhT[kMaxLayers], off_W3n;
   bool bwd;
 };
 
@@ -103,6 +103,9 @@ static WeightsLayout layout_weights(const Weights* W) {
     L.off_W3t = c.off; c.take<char>(static_cast<size_t>(W->cout) * W->Kp * W->cin_p * 2);
     for (int l = 2; l <= nl - 1; ++l) { L.off_WhT[l] = c.off; c.take<char>(static_cast<size_t>(W->kp[l]) * W->kp[l - 1] * 2); }
   }
+  if (W->prec == PREC_F16 || W->prec == PREC_BF16) {
+    L.off_W3n = c.off; c.take<char>(static_cast<size_t>(W->cin) * W->cout * W->Kp * 2);
+  }
   L.bytes = c.off;
   return L;
 }
@@ -156,6 +159,11 @@ int weights_prepare(Weights* W, int n_layers, const int* dims, int cin, int cout
   if (s) return s;
   W->W3p = W3p;
   W->B3 = B3;
+  if (prec == PREC_F16 || prec == PREC_BF16) {
+    s = launch_pad_convert(prec, Wsrc[nl - 1], cin * cout, W->K, base + L.off_W3n, cin * cout, W->Kp, st);
+    if (s) return s;
+    W->W3n = base + L.off_W3n;
+  }
   if (L.bwd) {
     s = launch_w3q(prec, Wsrc[nl - 1], cin, cout, W->K, W->Kp, W->cin_p, 0, base + L.off_W3q, st);
     if (s) return s;
@@ -289,6 +297,39 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
     }
   }
   return NNCONV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// formulation B: per-edge kernel matrices, for graphs whose sources have only a few out-edges.
+// Formulation C spends one [out, Kp] matrix per SOURCE (128 KB at out=64, Kp=1024) and a 128-row UMMA tile per
+// source; with 2-4 out-edges per node (the 1-D multipole hierarchy of config 5) that is as expensive as one kernel
+// matrix per EDGE and the tiles are 97 % empty.  K_e = W_L h_e + b_L is x-independent like h: it is built once per
+// (edge_attr, parameters) by the tcgen05 GEMM and every application is one bandwidth-bound pass over it.
+// ------------------------------------------------------------------------------------------------
+bool edge_kernels_supported(const Weights* W) {
+  return (W->prec == PREC_F16 || W->prec == PREC_BF16) && W->W3n != nullptr && (W->cin * W->cout) % 64 == 0 &&
+         W->cout % 2 == 0 && W->n_layers >= 2;
+}
+
+size_t edge_kernels_bytes(const Plan* P, const Weights* W) {
+  return static_cast<size_t>(P->E > 0 ? P->E : 1) * W->cin * W->cout * 2 + 1024;
+}
+
+int edge_kernels(const Plan* P, const Weights* W, const void* h, void* Kmat, cudaStream_t st) {
+  NNC_REQUIRE(edge_kernels_supported(W), NNCONV_ERR_UNSUPPORTED, "per-edge kernel matrices: unsupported shape / precision");
+  if (P->E == 0) return NNCONV_OK;
+  const int64_t hpad = round_up64(P->E, 128);
+  const int NK = W->cin * W->cout;
+  return launch_gemm_tc(W->prec, h, P->E, 0, static_cast<int>(P->E), W->Kp, W->W3n, NK, W->B3, 0, Kmat, NK, st, nullptr, 0, 0,
+                        0, nullptr, nullptr, 0, 0, hpad);
+}
+
+int apply_edge(const Plan* P, const Weights* W, const void* Kmat, const float* x, const float* root, const float* bias,
+               int aggr_mean, float* out, cudaStream_t st) {
+  int s = launch_out_init(x, root, bias, P->N, W->cin, W->cout, out, st);
+  if (s) return s;
+  if (P->E == 0 || P->n_src == 0) return NNCONV_OK;
+  return launch_apply_edge(W->prec, P, W, Kmat, x, aggr_mean, out, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -619,6 +660,25 @@ int nnconv_edge_features_overflow(const void* ws, void* stream, int64_t* count) 
   NNC_CHECK_CUDA(cudaStreamSynchronize(st));
   *count = v;
   return NNCONV_OK;
+}
+
+int nnconv_edge_kernels_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t* bytes) {
+  NNC_REQUIRE(plan && w && bytes, NNCONV_ERR_ARG, "null pointer");
+  NNC_REQUIRE(edge_kernels_supported(&w->w), NNCONV_ERR_UNSUPPORTED, "per-edge kernel matrices: unsupported shape / precision");
+  *bytes = edge_kernels_bytes(&plan->p, &w->w);
+  return NNCONV_OK;
+}
+
+int nnconv_edge_kernels(const nnconv_plan_t* plan, const nnconv_weights_t* w, const void* h, void* kmat, void* stream) {
+  NNC_REQUIRE(plan && w && kmat && (h || plan->p.E == 0), NNCONV_ERR_ARG, "null pointer");
+  return edge_kernels(&plan->p, &w->w, h, kmat, static_cast<cudaStream_t>(stream));
+}
+
+int nnconv_apply_edge(const nnconv_plan_t* plan, const nnconv_weights_t* w, const void* kmat, const float* x,
+                      const float* root, const float* bias, int aggr, float* out, void* stream) {
+  NNC_REQUIRE(plan && w && x && out && (kmat || plan->p.E == 0), NNCONV_ERR_ARG, "null pointer");
+  NNC_REQUIRE(aggr == NNCONV_AGGR_ADD || aggr == NNCONV_AGGR_MEAN, NNCONV_ERR_UNSUPPORTED, "aggr must be add or mean");
+  return apply_edge(&plan->p, &w->w, kmat, x, root, bias, aggr == NNCONV_AGGR_MEAN, out, static_cast<cudaStream_t>(stream));
 }
 
 int nnconv_apply_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t want_y_bytes, size_t* ws_bytes) {

@@ -48,6 +48,8 @@ struct GemmTcArgs {
   // chunk (c / 64) + N / 64 (chunk-major).
   int a_split_nk;
   int c_split;
+  int64_t a_chunk_rows_pad;   // > 0: A is chunk-major [K/64][a_chunk_rows_pad][64] (the edge-feature layout): K block kb of
+                              // row r is the box at (0, kb * a_chunk_rows_pad + r) of the [K/64 * rows_pad, 64] view
   int* overflow;       // counts 32-column pieces holding a value beyond the fp16 range (fp16 outputs only), or nullptr
   // backward epilogues: mask != nullptr -> C[r, c] = mask16[r * mask_ld + c] > 0 ? acc : 0 (ReLU derivative taken
   // from the stored 16-bit activation); out_f32 -> C is fp32 [M, ldc], plain stores, no conversion.
@@ -144,8 +146,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (elect_one()) {
           mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
           const int ka = (a.a_split_nk > 0 && kb >= a.a_split_nk) ? kb - a.a_split_nk : kb;
-          tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full[stage], ka * Cfg::kBlockK,
-                      a.a_row0 + mb * Cfg::kBlockM, kEvictNormal);
+          if (a.a_chunk_rows_pad > 0)
+            tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full[stage], 0,
+                        static_cast<int>(ka * a.a_chunk_rows_pad) + a.a_row0 + mb * Cfg::kBlockM, kEvictNormal);
+          else
+            tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full[stage], ka * Cfg::kBlockK,
+                        a.a_row0 + mb * Cfg::kBlockM, kEvictNormal);
           tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full[stage], kb * Cfg::kBlockK, nb * BLOCK_N,
                       kEvictLast);
         }
@@ -380,7 +386,7 @@ int tc_num_sms() { return g_num_sms; }
 int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a_row0, int M, int K, const void* B,
                    int N, const float* bias, int relu, void* C, int64_t ldc, cudaStream_t st, const PipeFlags* pf,
                    int64_t chunk_rows_pad, int64_t c_row0, int split_flags, int* overflow, const void* mask,
-                   int64_t mask_ld, int out_f32) {
+                   int64_t mask_ld, int out_f32, int64_t a_chunk_rows_pad) {
   if (M <= 0 || N <= 0) return NNCONV_OK;
   int s = tc_init();
   if (s != NNCONV_OK) return s;
@@ -396,8 +402,14 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
   const bool small = pf && pf->small_footprint && N >= 128;
   const int BN = small ? 128 : (N % 256 == 0 || N > 256) ? 256 : (N % 128 == 0 || N > 128) ? 128 : 64;
   CUtensorMap tmA, tmB;
-  s = make_tmap_2d_16b(&tmA, bf, A_base, static_cast<uint64_t>(a_rows_total),
-                       static_cast<uint64_t>(a_split ? K / 3 * 2 : K), 128);
+  if (a_chunk_rows_pad > 0) {
+    NNC_REQUIRE(!a_split && static_cast<int64_t>(K / 64) * a_chunk_rows_pad < (int64_t(1) << 31), NNCONV_ERR_ARG,
+                "gemm_tc: chunk-major A too large / not splittable");
+    s = make_tmap_2d_16b(&tmA, bf, A_base, static_cast<uint64_t>(K / 64) * static_cast<uint64_t>(a_chunk_rows_pad), 64, 128);
+  } else {
+    s = make_tmap_2d_16b(&tmA, bf, A_base, static_cast<uint64_t>(a_rows_total),
+                         static_cast<uint64_t>(a_split ? K / 3 * 2 : K), 128);
+  }
   if (s != NNCONV_OK) return s;
   s = make_tmap_2d_16b(&tmB, bf, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), BN);
   if (s != NNCONV_OK) return s;
@@ -405,6 +417,7 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
   a.M = M; a.N = N; a.K = K; a.a_row0 = static_cast<int>(a_row0); a.bias = bias; a.relu = relu; a.C = C; a.ldc = ldc;
   a.chunk_rows_pad = chunk_rows_pad;
   a.c_row0 = c_row0;
+  a.a_chunk_rows_pad = a_chunk_rows_pad;
   a.a_split_nk = a_split ? K / 192 : 0;
   a.c_split = c_split ? 1 : 0;
   a.overflow = (overflow != nullptr && !bf) ? overflow : nullptr;

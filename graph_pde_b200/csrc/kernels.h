@@ -59,7 +59,12 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
                    const void* B, int N, const float* bias, int relu, void* C, int64_t ldc, cudaStream_t st,
                    const PipeFlags* pf = nullptr, int64_t chunk_rows_pad = 0, int64_t c_row0 = 0,
                    int split_flags = 0, int* overflow = nullptr, const void* mask = nullptr, int64_t mask_ld = 0,
-                   int out_f32 = 0);
+                   int out_f32 = 0, int64_t a_chunk_rows_pad = 0);
+
+// ---- per-edge kernel matrices (formulation B, for graphs with few out-edges per source): K_e = W_L h_e + b_L once per
+// (edge_attr, parameters), then out[dst] += x_src . K_e per application (kernels_simt.cu)
+int launch_apply_edge(int prec, const Plan* P, const Weights* W, const void* Kmat, const float* x, int aggr_mean, float* out,
+                      cudaStream_t st);
 
 // ---- gemm_tn.cu (tcgen05, MN-major operands): C[M, N] fp32 += alpha * sum_{r<R} A[r, a_col0 + m] * B[r, b_col0 + n]
 // (A: [R, lda], B: [R, ldb] 16-bit row-major; C accumulates with fp32 atomics, the caller zero-initialises it)

@@ -61,6 +61,7 @@ struct Weights {
   const void* W3p;              // [cout*Kp, cin_p] in `prec`:  W3p[(o*Kp + k), i] = W_L[i*cout + o, k] (split: 3*cin_p columns)
   const float* B3;              // [cin, cout] fp32 = b_L viewed (in, out)
   // extra images for the tensor-core backward (16-bit, non-split precisions only; nullptr otherwise)
+  const void* W3n;              // [cin*cout, Kp]: the last Linear in its own layout, padded (per-edge kernel matrices)
   const void* W3q;              // [Kp*cout, cin_p]:  W3q[(k*cout + o), i] = W_L[i*cout + o, k]   (Y^T rows per source)
   const void* W3t;              // [cin_p, Kp*cout]:  W3t[i, (k*cout + o)] = W_L[i*cout + o, k]   (dx = dY : W_L)
   const void* WhT[kMaxLayers];  // hidden layers l = 2 .. L-1 transposed: [kp[l-1], kp[l]]       (dz_{l-1} = dz_l W_l)
@@ -92,6 +93,13 @@ size_t backward_mlp_ws_bytes(const Plan* P, const Weights* W, int T, size_t want
 int backward_mlp_tc(const Plan* P, const Weights* W, const float* edge_attr, const void* h, int T,
                     const float* const* gouts, const float* const* xs_in, int aggr_mean, float* const* dWs,
                     float* const* dbs, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// per-edge kernel matrices for low out-degree graphs (formulation B): Kmat [E, cin*cout] 16-bit in sorted edge order
+size_t edge_kernels_bytes(const Plan* P, const Weights* W);
+bool edge_kernels_supported(const Weights* W);
+int edge_kernels(const Plan* P, const Weights* W, const void* h, void* Kmat, cudaStream_t st);
+int apply_edge(const Plan* P, const Weights* W, const void* Kmat, const float* x, const float* root, const float* bias,
+               int aggr_mean, float* out, cudaStream_t st);
 
 // backward of one application (fp32 CUDA-core path), backward.cu
 size_t backward_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes);

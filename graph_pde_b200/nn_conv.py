@@ -47,6 +47,10 @@ _BWD_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_WS_BYTES', str(2 << 30)))  #
 _BWD_APPLY_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_APPLY_WS_BYTES', str(9 << 30)))
 _BWD_MLP_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_MLP_WS_BYTES', str(6 << 30)))
 _BWD_MODE = os.environ.get('NNCONV_B200_BACKWARD', 'auto')       # auto | tc | fp32
+# per-edge kernel matrices (formulation B) for graphs with few out-edges per source: auto | on | off
+_EDGE_KERNELS = os.environ.get('NNCONV_B200_EDGE_KERNELS', 'auto')
+_EDGE_KERNELS_MAX_DEG = 8                       # auto: average out-degree of the sources with out-edges
+_EDGE_KERNELS_MAX_BYTES = 2 << 30
 
 
 def default_precision():
@@ -302,6 +306,7 @@ class NNConv_old(torch.nn.Module):
         self._prepared_key = None
         self._h_cache = collections.OrderedDict()
         self._h_cache_max = 1
+        self._k_cache = None
         self.reset_parameters()
 
     # -- reference: nn_conv.py:261-265 with torch_geometric.nn.inits.reset / uniform restated ----------
@@ -348,6 +353,7 @@ class NNConv_old(torch.nn.Module):
         self._prepared32_key = None
         self._prepared32 = None
         self._h_cache.clear()
+        self._k_cache = None
 
     def train(self, mode=True):
         self.invalidate()
@@ -366,6 +372,7 @@ class NNConv_old(torch.nn.Module):
             self._prepared = _Prepared(linears, self.in_channels, self.out_channels, precision)
             self._prepared_key = key
             self._h_cache.clear()
+            self._k_cache = None
         return self._prepared
 
     def edge_features(self, plan, prepared, edge_attr):
@@ -380,6 +387,7 @@ class NNConv_old(torch.nn.Module):
                                                 ctypes.byref(ws_b)))
         dev = edge_attr.device
         self._h_cache.clear()                       # free the previous sample's features first
+        self._k_cache = None
         h = torch.empty(h_b.value, dtype=torch.uint8, device=dev)
         ws = torch.empty(ws_b.value, dtype=torch.uint8, device=dev)
         n_l = ctypes.c_int64(0)
@@ -423,9 +431,41 @@ class NNConv_old(torch.nn.Module):
         h = self.edge_features(plan, prepared, ea32)
         return plan, prepared, ea32, h
 
+    def _edge_kernels(self, plan, prepared, h):
+        """K_e = W_L h_e + b_L for every edge (formulation B) when the graph has few out-edges per source, else None.
+        Cached with h: as x-independent as the edge features."""
+        if _EDGE_KERNELS == 'off' or prepared.precision not in ('f16', 'fp16', 'bf16') or plan.E == 0:
+            return None
+        if _EDGE_KERNELS != 'on' and not (plan.E <= _EDGE_KERNELS_MAX_DEG * max(plan.n_src, 1) and
+                                          plan.E * self.in_channels * self.out_channels * 2 <= _EDGE_KERNELS_MAX_BYTES):
+            return None
+        hit = getattr(self, '_k_cache', None)
+        if hit is not None and hit[0] is h:
+            return hit[1]
+        L = _lib.lib()
+        nbytes = ctypes.c_size_t()
+        if L.nnconv_edge_kernels_sizes(plan.handle, prepared.handle, ctypes.byref(nbytes)) != _lib.OK:
+            return None                                   # shape not covered: formulation C
+        kmat = torch.empty(nbytes.value, dtype=torch.uint8, device=h.device)
+        _lib.check(L.nnconv_edge_kernels(plan.handle, prepared.handle, _ptr(h), _ptr(kmat), _stream_ptr(h.device)))
+        stats['launches'] += 1
+        stats['edge_kernel_passes'] = stats.get('edge_kernel_passes', 0) + 1
+        self._k_cache = (h, kmat)
+        return kmat
+
     def _apply_impl(self, plan, prepared, h, x32):
         L = _lib.lib()
         dev = x32.device
+        kmat = self._edge_kernels(plan, prepared, h)
+        if kmat is not None:
+            out = torch.empty(x32.size(0), self.out_channels, dtype=torch.float32, device=dev)
+            root = self.root.detach().contiguous().float() if self.root is not None else None
+            bias = self.bias.detach().contiguous().float() if self.bias is not None else None
+            _lib.check(L.nnconv_apply_edge(plan.handle, prepared.handle, _ptr(kmat), _ptr(x32), _ptr(root), _ptr(bias),
+                                           _lib.AGGR[self.aggr], _ptr(out), _stream_ptr(dev)))
+            stats['launches'] += 2
+            stats['applies'] += 1
+            return out
         ws_b = ctypes.c_size_t()
         _lib.check(L.nnconv_apply_sizes(plan.handle, prepared.handle, _Y_BYTES, ctypes.byref(ws_b)))
         ws = torch.empty(ws_b.value, dtype=torch.uint8, device=dev)

@@ -114,6 +114,16 @@ int nnconv_edge_features(const nnconv_plan_t* plan, const nnconv_weights_t* w, c
  * Copies one int to the host and synchronises `stream`.  A non-zero count means h holds inf: use bf16 / fp32. */
 int nnconv_edge_features_overflow(const void* ws, void* stream, int64_t* count);
 
+/* ---- per-edge kernel matrices for graphs with few out-edges per source (the 1-D multipole hierarchy of
+ * MGKN_orthogonal_burgers1d.py has 2-4): K_e = W_L h_e + b_L ([in, out] 16-bit per edge, sorted edge order) is as
+ * x-independent as h, so it is built ONCE per (edge_attr, parameters) from the h of nnconv_edge_features
+ * (nn_conv.py:274) and every application is nnconv_apply_edge: out[dst] (+)= x_src @ K_e, one bandwidth-bound pass
+ * (nn_conv.py:275-282 incl. root / bias / mean).  Same result as nnconv_apply up to 16-bit rounding of K_e. */
+int nnconv_edge_kernels_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t* bytes);
+int nnconv_edge_kernels(const nnconv_plan_t* plan, const nnconv_weights_t* w, const void* h, void* kmat, void* stream);
+int nnconv_apply_edge(const nnconv_plan_t* plan, const nnconv_weights_t* w, const void* kmat, const float* x,
+                      const float* root, const float* bias, int aggr, float* out, void* stream);
+
 /* ---- one NNConv application: gather + last Linear + per-edge contraction + scatter + root + bias --- */
 int nnconv_apply_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t want_y_bytes, size_t* ws_bytes);
 /* x [N,in] fp32, root [in,out] or NULL, bias [out] or NULL, out [N,out] fp32 (fully overwritten). */

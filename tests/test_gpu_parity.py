@@ -267,3 +267,35 @@ def test_node_features_beyond_fp16_range(dev, precision, knob, lib_options):
         out4 = conv((4.0 * x).to(dev), ei.to(dev), ea.to(dev))
     lin_ref = 4.0 * (out - bias.to(dev)) + bias.to(dev)
     assert rel_err(out4, lin_ref) < 1e-5
+
+
+@pytest.mark.parametrize('precision', ['f16', 'bf16'])
+def test_low_out_degree_graph_uses_per_edge_kernel_matrices(dev, precision):
+    """The 1-D multipole stencils of MGKN_orthogonal_burgers1d.py give every node 2-4 out-edges: the conv switches
+    to formulation B (K_e built once by the tcgen05 GEMM, one streaming pass per application) and must agree with
+    the oracle and with formulation C on the same inputs."""
+    from graph_pde_b200 import graphs, nn_conv
+    s, w, kw = 512, 64, 128
+    X, eis, eas = graphs.multi_pole_grid1d(torch.randn(s, generator=torch.Generator().manual_seed(0)), s, is_periodic=True,
+                                           levels=3)
+    ei, ea = eis[1], eas[1]                          # interactive neighbours of the finest level: 4 out-edges per node
+    ws, bs, root, bias = O.reference_init(w, w, [4, kw, kw, w * w], True, True, seed=4)
+    x = torch.randn(s, w, generator=torch.Generator().manual_seed(1))
+    ref = O.nnconv_forward(x, ei, ea, ws, bs, root, bias, 'mean')
+    conv = make_conv(_conv_cls(), ws, bs, root, bias, 'mean', w, w, precision, dev)
+    n0 = nn_conv.stats.get('edge_kernel_passes', 0)
+    with torch.no_grad():
+        out_b = conv(x.to(dev), ei.to(dev), ea.to(dev))
+        out_b2 = conv(2.0 * x.to(dev), ei.to(dev), ea.to(dev))       # second application reuses K_e
+    assert nn_conv.stats.get('edge_kernel_passes', 0) == n0 + 1
+    assert rel_err(out_b, ref) < TOL[precision]
+    assert rel_err(out_b2 - bias.to(dev), 2.0 * (out_b - bias.to(dev))) < 1e-5
+    old = nn_conv._EDGE_KERNELS
+    nn_conv._EDGE_KERNELS = 'off'
+    try:
+        conv_c = make_conv(_conv_cls(), ws, bs, root, bias, 'mean', w, w, precision, dev)
+        with torch.no_grad():
+            out_c = conv_c(x.to(dev), ei.to(dev), ea.to(dev))
+    finally:
+        nn_conv._EDGE_KERNELS = old
+    assert rel_err(out_b, out_c) < 2 * TOL[precision]
