@@ -236,3 +236,102 @@ def partitioned_conv_stack_peer(conv_fn, x_local, part, edge_attr_local, depth, 
             x = torch.relu(out) if relu else out
     halo.finish()
     return x[part.own_lo:part.own_hi]
+
+
+# ------------------------------------------------------------------------------------------------------
+# 1-D aligned node-range partition of the multipole hierarchy (BASELINE config 5: orthogonal MGKN, Burgers 1-D,
+# multipole-graph-neural-operator/MGKN_orthogonal_burgers1d.py:59-86 on multi_pole_grid1d, utilities.py:1702-1769)
+# ------------------------------------------------------------------------------------------------------
+class Range1DPartition(object):
+    """Rank r owns the finest-level nodes [lo, hi) with lo, hi multiples of 2^(levels-1), hence nodes
+    [lo >> j, hi >> j) of level j: avg_pool1d(2) restriction and nearest-neighbour prolongation stay local.  The
+    stencils reach |offset| <= 3 (utilities.py:1749), so every level carries ``halo`` = 3 nodes per side
+    (periodic wrap when the mesh is periodic); edges are owned by their DESTINATION.  Local layout per level:
+    [halo_left | owned | halo_right]."""
+
+    def __init__(self, s, levels, rank, world, halo=3, periodic=True):
+        self.s, self.levels, self.rank, self.world, self.halo, self.periodic = s, levels, rank, world, halo, periodic
+        align = 2 ** (levels - 1)
+        blocks = s // align
+        cuts = [(blocks * k) // world * align for k in range(world + 1)]
+        self.lo, self.hi = cuts[rank], cuts[rank + 1]
+        if min(b - a for a, b in zip(cuts[:-1], cuts[1:])) >> (levels - 1) < halo:
+            raise ValueError('ranges narrower than the halo on the coarsest level')
+
+    def owned(self, j):
+        return self.lo >> j, self.hi >> j
+
+    def n_local(self, j):
+        a, b = self.owned(j)
+        return (b - a) + 2 * self.halo
+
+    def local_edges(self, j, edge_index):
+        """Edges of level j that END in an owned node, in the global order, renumbered locally.  Returns
+        (edge_index_local, mask) -- mask selects the matching rows of edge_attr."""
+        a, b = self.owned(j)
+        n = self.s >> j
+        mask = (edge_index[1] >= a) & (edge_index[1] < b)
+        e = edge_index[:, mask]
+        base = a - self.halo
+        loc = (e - base) % n if self.periodic else (e - base)
+        return loc.contiguous(), mask
+
+    def with_halos(self, owned_rows, group=None):
+        """owned_rows: list over levels of [owned_j, C] tensors -> list of [halo + owned_j + halo, C]; ONE
+        all-gather of every level's 2*halo boundary rows."""
+        h = self.halo
+        send = torch.cat([torch.cat([x[:h], x[-h:]], dim=0) for x in owned_rows], dim=0).contiguous()
+        if self.world > 1:
+            bufs = [torch.empty_like(send) for _ in range(self.world)]
+            dist.all_gather(bufs, send, group=group)
+        else:
+            bufs = [send]
+        left, right = bufs[(self.rank - 1) % self.world], bufs[(self.rank + 1) % self.world]
+        out = []
+        for j, x in enumerate(owned_rows):
+            o = 2 * h * j
+            hl = left[o + h:o + 2 * h]          # the left neighbour's LAST h owned rows
+            hr = right[o:o + h]                 # the right neighbour's FIRST h owned rows
+            if not self.periodic:
+                if self.rank == 0:
+                    hl = torch.zeros_like(hl)
+                if self.rank == self.world - 1:
+                    hr = torch.zeros_like(hr)
+            out.append(torch.cat([hl, x, hr], dim=0))
+        return out
+
+
+def partitioned_mgkn_forward(part, X0_owned, edge_index_local, edge_attr_local, convs, fc1, fc2, fc3, depth, width,
+                             group=None):
+    """MGKN.forward (MGKN_orthogonal_burgers1d.py:59-86) on one rank's node range.  ``convs[l](x_local, ei, ea)``
+    returns [n_local, width] (owned rows valid); ``edge_index_local[l]`` / ``edge_attr_local[l]`` come from
+    ``part.local_edges``: set l >= 1 acts on level l-1, set 0 on level 0, the LAST set on the coarsest level.
+    One halo exchange (all levels in one all-gather) per depth iteration; restriction / prolongation are local."""
+    import torch.nn.functional as F
+    level = len(edge_index_local) - 1
+    h = part.halo
+
+    def down(x):
+        return F.avg_pool1d(x.t().unsqueeze(0), kernel_size=2).squeeze(0).t()
+
+    def up(x):
+        return x.repeat_interleave(2, dim=0)
+
+    def own(t):
+        return t[h:t.size(0) - h]
+    x = fc1(X0_owned)
+    for _ in range(depth):
+        phi = []
+        for l in range(level):
+            phi.append(x)
+            if l != level - 1:
+                x = down(x)
+        phi_h = part.with_halos(phi, group)                        # the only communication of the iteration
+        x = torch.relu(x + own(convs[-1](phi_h[-1], edge_index_local[-1], edge_attr_local[-1])))
+        for l in reversed(range(level)):
+            if l != 0:
+                x = up(x)
+                x = torch.relu(x + own(convs[l](phi_h[l - 1], edge_index_local[l], edge_attr_local[l])))
+            else:
+                x = torch.relu(x + own(convs[0](phi_h[0], edge_index_local[0], edge_attr_local[0])))
+    return fc3(torch.relu(fc2(x)))

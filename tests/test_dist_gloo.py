@@ -140,3 +140,55 @@ def test_peer_halo_row_ranges_reproduce_the_all_gather_exchange():
             local[p.rank + 1][dst:dst + n] = x[src:src + n]
     for p, x in zip(parts, local):
         assert torch.equal(x, p.local_slice(xg)), p.rank
+
+
+def _mgkn1d_setup():
+    s, levels, width, depth = 128, 3, 8, 2
+    torch.manual_seed(0)
+    theta = torch.randn(s)
+    X, eis, eas = graphs.multi_pole_grid1d(theta, s, is_periodic=True, levels=levels)
+    p = {}
+    gen = torch.Generator().manual_seed(1)
+    p['fc1.weight'], p['fc1.bias'] = torch.randn(width, 2, generator=gen) * 0.5, torch.randn(width, generator=gen) * 0.1
+    p['fc2.weight'], p['fc2.bias'] = torch.randn(16, width, generator=gen) * 0.3, torch.randn(16, generator=gen) * 0.1
+    p['fc3.weight'], p['fc3.bias'] = torch.randn(1, 16, generator=gen) * 0.3, torch.randn(1, generator=gen) * 0.1
+    for l in range(levels + 1):
+        ws, bs, root, bias = O.reference_init(width, width, [4, 8, 8, width * width], seed=10 + l)
+        for i, (w, b) in enumerate(zip(ws, bs)):
+            p['conv_list.%d.nn.layers.%d.weight' % (l, 2 * i)] = w
+            p['conv_list.%d.nn.layers.%d.bias' % (l, 2 * i)] = b
+        p['conv_list.%d.root' % l], p['conv_list.%d.bias' % l] = root, bias
+    return s, levels, width, depth, X, eis, eas, p
+
+
+def _mgkn1d_job(rank, world):
+    import torch.nn.functional as F
+    s, levels, width, depth, X, eis, eas, p = _mgkn1d_setup()
+    part = partition.Range1DPartition(s, levels, rank, world, halo=3, periodic=True)
+    ei_loc, ea_loc = [], []
+    for l, (ei, ea) in enumerate(zip(eis, eas)):
+        j = 0 if l == 0 else l - 1
+        e, m = part.local_edges(j, ei)
+        ei_loc.append(e)
+        ea_loc.append(ea[m])
+
+    def mk(l):
+        ws, bs = O.mlp_params_from_state(p, 'conv_list.%d.nn.' % l)
+        return lambda x, ei, ea: O.nnconv_forward(x, ei, ea, ws, bs, p['conv_list.%d.root' % l], p['conv_list.%d.bias' % l], 'mean')
+    convs = [mk(l) for l in range(levels + 1)]
+    lin = lambda k: (lambda t: F.linear(t, p[k + '.weight'], p[k + '.bias']))   # noqa: E731
+    out = partition.partitioned_mgkn_forward(part, X[0][part.lo:part.hi], ei_loc, ea_loc, convs, lin('fc1'), lin('fc2'),
+                                             lin('fc3'), depth, width)
+    return (part.lo, part.hi, out.numpy())
+
+
+def test_range1d_partition_of_the_multipole_hierarchy_matches_unpartitioned():
+    """BASELINE config 5's decomposition: aligned node ranges, 3-node halos per level, one all-gather per depth
+    iteration -- partitioned MGKN forward == the oracle's unpartitioned forward."""
+    s, levels, width, depth, X, eis, eas, p = _mgkn1d_setup()
+    ref = O.mgkn_orthogonal_forward(X[0], eis, eas, p, depth, width, s).numpy()
+    parts = _run(_mgkn1d_job, 2)
+    got = np.zeros_like(ref)
+    for lo, hi, out in parts:
+        got[lo:hi] = out
+    np.testing.assert_allclose(got, ref, rtol=2e-5, atol=2e-6)
