@@ -48,7 +48,7 @@ static size_t esize_of(int prec) { return prec == PREC_FP32 ? 4 : 2; }
 // ------------------------------------------------------------------------------------------------
 struct WeightsLayout {
   size_t off_W1, off_b1, off_W1aug, off_Wh[kMaxLayers], off_bh[kMaxLayers], off_W3p, off_B3, bytes;
-  size_t off_W3q, off_W3t, off_WhT[kMaxLayers], off_W3n;
+  size_t off_W3q, off_W3t, off_WhT[kMaxLayers], off_W3n, off_wscale;
   bool bwd;
 };
 
@@ -93,6 +93,7 @@ static WeightsLayout layout_weights(const Weights* W) {
     L.off_Wh[l] = c.off; c.take<char>(static_cast<size_t>(W->kp[l]) * W->kp[l - 1] * W->esize * (W->split ? 3 : 1));
     L.off_bh[l] = c.off; c.take<float>(W->kp[l]);
   }
+  L.off_wscale = c.off; c.take<float>(2 * (kMaxLayers + 2));
   L.off_W3p = c.off; c.take<char>(static_cast<size_t>(W->cout) * W->Kp * W->cin_p * W->esize * (W->split ? 3 : 1));
   L.off_B3 = c.off; c.take<float>(static_cast<size_t>(W->cin) * W->cout);
   // images for the tensor-core backward (same conditions as backward_tc_supported)
@@ -141,10 +142,18 @@ int weights_prepare(Weights* W, int n_layers, const int* dims, int cin, int cout
       W->W1aug = aug;
     }
   }
+  float* wscale = reinterpret_cast<float*>(base + L.off_wscale);
+  if (W->split) W->wscale = wscale;
   for (int l = 2; l <= nl - 1; ++l) {
     void* Wh = base + L.off_Wh[l];
     float* bh = reinterpret_cast<float*>(base + L.off_bh[l]);
-    s = launch_pad_convert(prec, Wsrc[l - 1], dims[l], dims[l - 1], Wh, W->kp[l], W->kp[l - 1], st);
+    if (W->split) {
+      s = launch_pow2_scale(Wsrc[l - 1], static_cast<int64_t>(dims[l]) * dims[l - 1], wscale + 2 * l, st);
+      if (s) return s;
+      s = launch_pad_convert_split3(Wsrc[l - 1], dims[l], dims[l - 1], Wh, W->kp[l], W->kp[l - 1], wscale + 2 * l, st);
+    } else {
+      s = launch_pad_convert(prec, Wsrc[l - 1], dims[l], dims[l - 1], Wh, W->kp[l], W->kp[l - 1], st);
+    }
     if (s) return s;
     s = launch_pad_convert(PREC_FP32, bsrc[l - 1], 1, dims[l], bh, 1, W->kp[l], st);
     if (s) return s;
@@ -153,7 +162,11 @@ int weights_prepare(Weights* W, int n_layers, const int* dims, int cin, int cout
   }
   void* W3p = base + L.off_W3p;
   float* B3 = reinterpret_cast<float*>(base + L.off_B3);
-  s = launch_w3p(prec, Wsrc[nl - 1], cin, cout, W->K, W->Kp, W->cin_p, W3p, st);
+  if (W->split) {
+    s = launch_pow2_scale(Wsrc[nl - 1], static_cast<int64_t>(dims[nl]) * dims[nl - 1], wscale + 2 * nl, st);
+    if (s) return s;
+  }
+  s = launch_w3p(prec, Wsrc[nl - 1], cin, cout, W->K, W->Kp, W->cin_p, W3p, st, W->split ? wscale + 2 * nl : nullptr);
   if (s) return s;
   s = launch_pad_convert(PREC_FP32, bsrc[nl - 1], 1, cin * cout, B3, 1, cin * cout, st);
   if (s) return s;
@@ -289,7 +302,8 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
       } else {
         s = launch_gemm_tc(W->prec, cur, n, 0, static_cast<int>(n), kmul * W->kp[l - 1], W->Wh[l], W->kp[l], W->bh[l], 1,
                            dst, static_cast<int64_t>(amul) * W->kp[l], st, nullptr, last ? hpad : 0, e0,
-                           W->split ? (GEMM_A_SPLIT | GEMM_C_SPLIT) : 0, overflow);
+                           W->split ? (GEMM_A_SPLIT | GEMM_C_SPLIT) : 0, overflow, nullptr, 0, 0, 0,
+                           W->split ? W->wscale + 2 * l + 1 : nullptr);
       }
       if (s) return s;
       if (launches) ++*launches;

@@ -56,6 +56,7 @@ struct ApplyArgs {
   // [cout][hi(Kp) | lo(Kp)], and contraction step j = 3q + r pairs (A, B) = (hi_q, Yhi_q), (hi_q, Ylo_q), (lo_q, Yhi_q)
   int split_nk;
   int Kp;
+  const float* y_scale;   // PREC_F16X2: inverse of the power-of-two scale of the stored W3p (device scalar), or nullptr
   // Y GEMM
   int NY;                 // cout * Kp
   int num_kx;             // cin_p / 64
@@ -442,6 +443,7 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
       }
       const unsigned long long ty1 = a.trace.rec ? gtime() : 0ull;
       const int ymul = a.split_nk > 0 ? 2 : 1;
+      const float ysc = a.y_scale != nullptr ? __ldg(a.y_scale) : 1.f;
       uint16_t* ybase = reinterpret_cast<uint16_t*>(a.Yring) + static_cast<int64_t>(b % a.ring) * a.nb * a.NY * ymul;
       for (int i = static_cast<int>((blockIdx.x + 7u * b) % gridDim.x); i < tiles; i += gridDim.x, ++it) {
         const int mb = i / n_blocks, nbk = i % n_blocks;
@@ -465,7 +467,8 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
             uint32_t packed[16], packed_lo[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float f0 = __uint_as_float(vv[2 * j]), f1 = __uint_as_float(vv[2 * j + 1]);
+              float f0 = __uint_as_float(vv[2 * j]), f1 = __uint_as_float(vv[2 * j + 1]);
+              if (FMT == 0 && a.split_nk > 0) { f0 *= ysc; f1 *= ysc; }
               if (FMT == 0) {
                 __half2 hh = __floats2half2_rn(f0, f1);
                 packed[j] = *reinterpret_cast<uint32_t*>(&hh);
@@ -641,6 +644,7 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
   a.e_pad = static_cast<int>(e_pad);
   a.split_nk = split ? W->Kp / 64 : 0;
   a.Kp = W->Kp;
+  a.y_scale = (split && W->wscale) ? W->wscale + 2 * W->n_layers + 1 : nullptr;
   a.NY = NY; a.num_kx = xmul * W->cin_p / 64; a.Yring = Yring;
   a.y_store_policy = opt.y_store_policy == 1 ? kEvictLast : opt.y_store_policy == 2 ? kEvictFirst : kEvictNormal;
   a.debug_scatter = opt.debug_scatter;   // wrong results, timing only

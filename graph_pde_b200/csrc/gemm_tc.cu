@@ -48,6 +48,7 @@ struct GemmTcArgs {
   // chunk (c / 64) + N / 64 (chunk-major).
   int a_split_nk;
   int c_split;
+  const float* acc_scale;     // optional device scalar multiplied into the fp32 accumulator before bias (exact power of two)
   int64_t a_chunk_rows_pad;   // > 0: A is chunk-major [K/64][a_chunk_rows_pad][64] (the edge-feature layout): K block kb of
                               // row r is the box at (0, kb * a_chunk_rows_pad + r) of the [K/64 * rows_pad, 64] view
   int* overflow;       // counts 32-column pieces holding a value beyond the fp16 range (fp16 outputs only), or nullptr
@@ -212,6 +213,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       uint32_t v[2][32];
       tmem_ld32(tbase, v[0]);
       tmem_ld_wait();
+      const float accs = (EPI == EPI_SPLIT && a.acc_scale != nullptr) ? __ldg(a.acc_scale) : 1.f;
       const bool use_tma = Cfg::kStoreBytes > 0 && a.tma_store != 0;
       // this warp's staging: 2 buffers of 32 rows x 64 B; 16-byte unit u of row r sits at (u ^ ((r >> 1) & 3))
       // (SWIZZLE_64B of tmC) -- conflict-free for the 8-lane phases of a v4 shared store
@@ -229,6 +231,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           for (int j4 = 0; j4 < 8; ++j4) {
             float f[4] = {__uint_as_float(vv[4 * j4]), __uint_as_float(vv[4 * j4 + 1]),
                           __uint_as_float(vv[4 * j4 + 2]), __uint_as_float(vv[4 * j4 + 3])};
+            if (EPI == EPI_SPLIT) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) f[q] *= accs;
+            }
             if (a.bias) {
               if (a.bias_v4) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + col0) + j4);
@@ -386,7 +392,7 @@ int tc_num_sms() { return g_num_sms; }
 int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a_row0, int M, int K, const void* B,
                    int N, const float* bias, int relu, void* C, int64_t ldc, cudaStream_t st, const PipeFlags* pf,
                    int64_t chunk_rows_pad, int64_t c_row0, int split_flags, int* overflow, const void* mask,
-                   int64_t mask_ld, int out_f32, int64_t a_chunk_rows_pad) {
+                   int64_t mask_ld, int out_f32, int64_t a_chunk_rows_pad, const float* acc_scale) {
   if (M <= 0 || N <= 0) return NNCONV_OK;
   int s = tc_init();
   if (s != NNCONV_OK) return s;
@@ -418,6 +424,7 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
   a.chunk_rows_pad = chunk_rows_pad;
   a.c_row0 = c_row0;
   a.a_chunk_rows_pad = a_chunk_rows_pad;
+  a.acc_scale = acc_scale;
   a.a_split_nk = a_split ? K / 192 : 0;
   a.c_split = c_split ? 1 : 0;
   a.overflow = (overflow != nullptr && !bf) ? overflow : nullptr;

@@ -7,7 +7,11 @@ namespace nnc {
 
 // ---- kernels_simt.cu (CUDA cores)
 int launch_pad_convert(int prec, const float* src, int R, int C, void* dst, int Rp, int Cp, cudaStream_t st);
-int launch_w3p(int prec, const float* WL, int cin, int cout, int K, int Kp, int cin_p, void* dst, cudaStream_t st);
+int launch_w3p(int prec, const float* WL, int cin, int cout, int K, int Kp, int cin_p, void* dst, cudaStream_t st,
+               const float* scale = nullptr);
+// scale2[0] = power of two s with max|src| * s in [0.5, 1), scale2[1] = 1 / s   (device floats)
+int launch_pow2_scale(const float* src, int64_t n, float* scale2, cudaStream_t st);
+int launch_pad_convert_split3(const float* src, int R, int C, void* dst, int Rp, int Cp, const float* scale, cudaStream_t st);
 // backward images of the last Linear: transposed == 0 -> W3q [Kp*cout, cin_p], 1 -> W3t [cin_p, Kp*cout]
 int launch_w3q(int prec, const float* WL, int cin, int cout, int K, int Kp, int cin_p, int transposed, void* dst,
                cudaStream_t st);
@@ -59,7 +63,7 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
                    const void* B, int N, const float* bias, int relu, void* C, int64_t ldc, cudaStream_t st,
                    const PipeFlags* pf = nullptr, int64_t chunk_rows_pad = 0, int64_t c_row0 = 0,
                    int split_flags = 0, int* overflow = nullptr, const void* mask = nullptr, int64_t mask_ld = 0,
-                   int out_f32 = 0, int64_t a_chunk_rows_pad = 0);
+                   int out_f32 = 0, int64_t a_chunk_rows_pad = 0, const float* acc_scale = nullptr);
 
 // ---- per-edge kernel matrices (formulation B, for graphs with few out-edges per source): K_e = W_L h_e + b_L once per
 // (edge_attr, parameters), then out[dst] += x_src . K_e per application (kernels_simt.cu)

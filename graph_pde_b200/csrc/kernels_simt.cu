@@ -79,16 +79,40 @@ __device__ __forceinline__ __half split_part(float v, int part) {
   return part == 1 ? __float2half_rn(v - __half2float(hi)) : hi;
 }
 __global__ void k_pad_convert_split3(const float* __restrict__ src, int R, int C, __half* __restrict__ dst, int Rp,
-                                     int Cp) {
+                                     int Cp, const float* __restrict__ scale) {
   int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<int64_t>(Rp) * 3 * Cp) return;
   const int r = static_cast<int>(i / (3 * Cp)), cc = static_cast<int>(i % (3 * Cp));
   const int part = cc / Cp, c = cc % Cp;
-  const float v = (r < R && c < C) ? src[static_cast<int64_t>(r) * C + c] : 0.f;
+  const float sc = scale ? scale[0] : 1.f;
+  const float v = (r < R && c < C) ? src[static_cast<int64_t>(r) * C + c] * sc : 0.f;
   dst[i] = split_part(v, part);
 }
+// scale2[0] = 2^k with max|src| * 2^k in [0.5, 1) (1 for an all-zero / non-finite matrix), scale2[1] = 2^-k
+__global__ void k_absmax_bits(const float* __restrict__ src, int64_t n, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float a = fabsf(src[i]);
+    if (a <= 3.0e38f) m = fmaxf(m, a);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+__global__ void k_pow2_from_max(float* scale2) {
+  const float m = scale2[0];
+  float s = 1.f;
+  if (m > 0.f && m <= 3.0e38f) {
+    int e;
+    frexpf(m, &e);                  // m = f * 2^e, f in [0.5, 1)  ->  m * 2^-e in [0.5, 1)
+    e = e < -60 ? -60 : (e > 60 ? 60 : e);
+    s = ldexpf(1.f, -e);
+  }
+  scale2[0] = s;
+  scale2[1] = 1.f / s;
+}
 __global__ void k_w3p_split3(const float* __restrict__ WL, int cin, int cout, int K, int Kp, int cin_p,
-                             __half* __restrict__ dst) {
+                             __half* __restrict__ dst, const float* __restrict__ scale) {
   int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t total = static_cast<int64_t>(cout) * Kp * 3 * cin_p;
   if (idx >= total) return;
@@ -97,7 +121,7 @@ __global__ void k_w3p_split3(const float* __restrict__ WL, int cin, int cout, in
   const int64_t ok = idx / (3 * cin_p);
   const int k = static_cast<int>(ok % Kp);
   const int o = static_cast<int>(ok / Kp);
-  const float v = (i < cin && k < K) ? WL[(static_cast<int64_t>(i) * cout + o) * K + k] : 0.f;
+  const float v = (i < cin && k < K) ? WL[(static_cast<int64_t>(i) * cout + o) * K + k] * (scale ? scale[0] : 1.f) : 0.f;
   dst[idx] = split_part(v, part);
 }
 
@@ -443,7 +467,8 @@ int launch_pad_convert(int prec, const float* src, int R, int C, void* dst, int 
   if (prec == PREC_F16X2) {
     const int64_t total = static_cast<int64_t>(Rp) * 3 * Cp;
     if (total == 0) return NNCONV_OK;
-    k_pad_convert_split3<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(src, R, C, static_cast<__half*>(dst), Rp, Cp);
+    k_pad_convert_split3<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(src, R, C, static_cast<__half*>(dst), Rp, Cp,
+                                                                           nullptr);
     NNC_CHECK_LAUNCH();
     return NNCONV_OK;
   }
@@ -452,10 +477,33 @@ int launch_pad_convert(int prec, const float* src, int R, int C, void* dst, int 
   return launch_pad_convert_t<__nv_bfloat16>(src, R, C, dst, Rp, Cp, st);
 }
 
-int launch_w3p(int prec, const float* WL, int cin, int cout, int K, int Kp, int cin_p, void* dst, cudaStream_t st) {
+int launch_pad_convert_split3(const float* src, int R, int C, void* dst, int Rp, int Cp, const float* scale, cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(Rp) * 3 * Cp;
+  if (total == 0) return NNCONV_OK;
+  k_pad_convert_split3<<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(src, R, C, static_cast<__half*>(dst), Rp, Cp, scale);
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
+}
+
+int launch_pow2_scale(const float* src, int64_t n, float* scale2, cudaStream_t st) {
+  NNC_CHECK_CUDA(cudaMemsetAsync(scale2, 0, 2 * sizeof(float), st));
+  if (n > 0) {
+    int g = static_cast<int>(ceil_div64(n, 1024));
+    if (g > 592) g = 592;
+    k_absmax_bits<<<g, 256, 0, st>>>(src, n, reinterpret_cast<unsigned int*>(scale2));
+    NNC_CHECK_LAUNCH();
+  }
+  k_pow2_from_max<<<1, 1, 0, st>>>(scale2);
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
+}
+
+int launch_w3p(int prec, const float* WL, int cin, int cout, int K, int Kp, int cin_p, void* dst, cudaStream_t st,
+               const float* scale) {
   int64_t total = static_cast<int64_t>(cout) * Kp * cin_p;
   if (prec == PREC_F16X2) {
-    k_w3p_split3<<<(unsigned)ceil_div64(3 * total, 256), 256, 0, st>>>(WL, cin, cout, K, Kp, cin_p, static_cast<__half*>(dst));
+    k_w3p_split3<<<(unsigned)ceil_div64(3 * total, 256), 256, 0, st>>>(WL, cin, cout, K, Kp, cin_p, static_cast<__half*>(dst),
+                                                                       scale);
     NNC_CHECK_LAUNCH();
     return NNCONV_OK;
   }

@@ -61,6 +61,11 @@ struct Weights {
   const void* W3p;              // [cout*Kp, cin_p] in `prec`:  W3p[(o*Kp + k), i] = W_L[i*cout + o, k] (split: 3*cin_p columns)
   const float* B3;              // [cin, cout] fp32 = b_L viewed (in, out)
   // extra images for the tensor-core backward (16-bit, non-split precisions only; nullptr otherwise)
+  // PREC_F16X2: every split weight matrix is stored multiplied by a power of two that brings its largest entry
+  // into [0.5, 1) -- the lo halves of U(+-1/32)-sized weights would otherwise be fp16 subnormals (8 instead of 11
+  // bits) -- and the epilogue multiplies the fp32 accumulator by the inverse.  wscale[2*l] = scale of layer l's
+  // matrix (l = n_layers: the last Linear), wscale[2*l + 1] = its inverse; device floats, nullptr when not split.
+  const float* wscale;
   const void* W3n;              // [cin*cout, Kp]: the last Linear in its own layout, padded (per-edge kernel matrices)
   const void* W3q;              // [Kp*cout, cin_p]:  W3q[(k*cout + o), i] = W_L[i*cout + o, k]   (Y^T rows per source)
   const void* W3t;              // [cin_p, Kp*cout]:  W3t[i, (k*cout + o)] = W_L[i*cout + o, k]   (dx = dY : W_L)
