@@ -230,6 +230,7 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
   NNC_REQUIRE(ws != nullptr && ws_bytes >= kEfHeader, NNCONV_ERR_WORKSPACE, "edge_features: workspace too small");
   int* overflow = static_cast<int*>(ws);
   NNC_CHECK_CUDA(cudaMemsetAsync(overflow, 0, sizeof(int), st));
+  if (options().l2_reset) cudaCtxResetPersistingL2Cache();   // experiment knob: drop the Y ring's persisting lines
   if (E == 0) return NNCONV_OK;
   if (!options().overflow_check) overflow = nullptr;
   ws = static_cast<char*>(ws) + kEfHeader;

@@ -663,6 +663,8 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
       int dev = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+      if (opt.l2_persist > 1 && (static_cast<size_t>(opt.l2_persist) << 20) < static_cast<size_t>(max_persist))
+        max_persist = opt.l2_persist << 20;
       if (max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(max_persist));
     }
     const size_t ring_bytes = static_cast<size_t>(ring) * nb * NY * 2 * kmul;

@@ -143,15 +143,17 @@ __global__ void __launch_bounds__(256) k_xtv(const float* __restrict__ X, const 
 // dx[n, i] = sum_o g[n, o] * root[i, o]
 __global__ void k_g_rootT(const float* __restrict__ g, const float* __restrict__ root, int64_t N, int cin, int cout,
                           float* __restrict__ dx) {
-  extern __shared__ float sroot[];   // [cin][cout]
-  for (int i = threadIdx.x; i < cin * cout; i += blockDim.x) sroot[i] = root[i];
+  extern __shared__ float sroot[];   // [cin][cout + 1]: consecutive threads (i) hit consecutive banks
+  const int ld = cout + 1;
+  for (int i = threadIdx.x; i < cin * cout; i += blockDim.x) sroot[(i / cout) * ld + i % cout] = root[i];
   __syncthreads();
   const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (idx >= N * cin) return;
   const int64_t n = idx / cin;
   const int i = static_cast<int>(idx % cin);
+  const float* gr = g + n * cout;
   float acc = 0.f;
-  for (int o = 0; o < cout; ++o) acc = fmaf(g[n * cout + o], sroot[i * cout + o], acc);
+  for (int o = 0; o < cout; ++o) acc = fmaf(__ldg(gr + o), sroot[i * ld + o], acc);
   dx[idx] = acc;
 }
 
@@ -170,41 +172,31 @@ __global__ void k_colsum(const float* __restrict__ g, int64_t N, int C, float* _
   }
 }
 
-// Gs[c, o] = sum_{e in c} g[dst_e, o] * inv_deg[dst_e]
-__global__ void k_group_gsum(const float* __restrict__ g, const int* __restrict__ dst_sorted,
-                             const float* __restrict__ inv_deg, const int* __restrict__ group_ptr, int S, int cout,
-                             float* __restrict__ Gs) {
-  const int c = blockIdx.x * blockDim.y + threadIdx.y;
-  if (c >= S) return;
-  const int e0 = group_ptr[c], e1 = group_ptr[c + 1];
-  for (int o = threadIdx.x; o < cout; o += blockDim.x) {
-    float s = 0.f;
-    for (int e = e0; e < e1; ++e) {
-      const int d = dst_sorted[e];
-      s += g[static_cast<int64_t>(d) * cout + o] * (inv_deg ? inv_deg[d] : 1.f);
-    }
-    Gs[static_cast<int64_t>(c) * cout + o] = s;
-  }
-}
-
 // G16[t*128 + r, o] = (g[dst, o] * inv_deg[dst]) / gs  for r < cnt_t, zero rows up to 128 (cout == 64)
+// and, in the same pass, Gs[c, o] += sum of the tile's UNSCALED G rows (Gs zero-initialised by the caller)
 template <typename T16>
 __global__ void __launch_bounds__(256) k_gather_g16(const float* __restrict__ g, const int* __restrict__ dst_sorted,
-                                                    const float* __restrict__ inv_deg, const int* __restrict__ tile_e0,
+                                                    const float* __restrict__ inv_deg, const int* __restrict__ tile_c,
+                                                    const int* __restrict__ tile_e0,
                                                     const int* __restrict__ tile_cnt, const float* __restrict__ scal,
-                                                    T16* __restrict__ G16) {
+                                                    T16* __restrict__ G16, float* __restrict__ Gs) {
+  __shared__ float s_sum[32][65];
   const int t = blockIdx.x;
   const int e0 = tile_e0[t], cnt = tile_cnt[t];
   const float inv_gs = scal[2];
+  float colsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   // thread -> (row r = threadIdx / 8 + 32 * pass, 8 columns)
   for (int pass = 0; pass < 4; ++pass) {
     const int r = pass * 32 + threadIdx.x / 8, c0 = (threadIdx.x % 8) * 8;
     uint32_t w[4] = {0u, 0u, 0u, 0u};
     if (r < cnt) {
       const int d = dst_sorted[e0 + r];
-      const float sc = (inv_deg ? inv_deg[d] : 1.f) * inv_gs;
+      const float dsc = inv_deg ? inv_deg[d] : 1.f;
+      const float sc = dsc * inv_gs;
       const float4 a = *reinterpret_cast<const float4*>(g + static_cast<int64_t>(d) * 64 + c0);
       const float4 b = *reinterpret_cast<const float4*>(g + static_cast<int64_t>(d) * 64 + c0 + 4);
+      colsum[0] += a.x * dsc; colsum[1] += a.y * dsc; colsum[2] += a.z * dsc; colsum[3] += a.w * dsc;
+      colsum[4] += b.x * dsc; colsum[5] += b.y * dsc; colsum[6] += b.z * dsc; colsum[7] += b.w * dsc;
       if (std::is_same<T16, __half>::value) {
         w[0] = pack2<0>(a.x * sc, a.y * sc); w[1] = pack2<0>(a.z * sc, a.w * sc);
         w[2] = pack2<0>(b.x * sc, b.y * sc); w[3] = pack2<0>(b.z * sc, b.w * sc);
@@ -214,6 +206,19 @@ __global__ void __launch_bounds__(256) k_gather_g16(const float* __restrict__ g,
       }
     }
     *reinterpret_cast<uint4*>(G16 + (static_cast<int64_t>(t) * 128 + r) * 64 + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  // thread (rr = threadIdx / 8, cg = threadIdx % 8) holds the sums of rows rr, rr+32, rr+64, rr+96 for 8 columns
+  {
+    const int rr = threadIdx.x / 8, c0 = (threadIdx.x % 8) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_sum[rr][c0 + j] = colsum[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int rr = 0; rr < 32; ++rr) s += s_sum[rr][threadIdx.x];
+    atomicAdd(Gs + static_cast<int64_t>(tile_c[t]) * 64 + threadIdx.x, s);
   }
 }
 
@@ -233,12 +238,16 @@ __global__ void k_prep_xg(const float* __restrict__ x, const int* __restrict__ s
 __global__ void k_scatter_dx_tc(const float* __restrict__ dxp, int ld, const float* __restrict__ Gs,
                                 const float* __restrict__ B3, const int* __restrict__ src_nodes, int c0, int nb,
                                 int cin, int cout, const float* __restrict__ scal, float* __restrict__ dx) {
+  extern __shared__ float sb3[];     // [cin][cout + 1]
+  const int ldb = cout + 1;
+  for (int t = threadIdx.x; t < cin * cout; t += blockDim.x) sb3[(t / cout) * ldb + t % cout] = B3[t];
+  __syncthreads();
   const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<int64_t>(nb) * cin) return;
   const int c = static_cast<int>(i / cin), ii = static_cast<int>(i % cin);
   float acc = dxp[static_cast<int64_t>(c) * ld + ii] * scal[1];
   const float* gs = Gs + static_cast<int64_t>(c0 + c) * cout;
-  for (int o = 0; o < cout; ++o) acc = fmaf(B3[ii * cout + o], gs[o], acc);
+  for (int o = 0; o < cout; ++o) acc = fmaf(sb3[ii * ldb + o], __ldg(gs + o), acc);
   dx[static_cast<int64_t>(src_nodes[c0 + c]) * cin + ii] += acc;
 }
 
@@ -713,7 +722,7 @@ int backward_apply_tc(const Plan* P, const Weights* W, const void* h, const floa
     NNC_CHECK_CUDA(cudaMemsetAsync(droot, 0, sizeof(float) * cin * cout, st));
     k_xtv<<<(unsigned)ceil_div64(N, 32), 256, sizeof(float) * 32 * (cin + cout), st>>>(x, nullptr, gout, N, cin, cout, droot);
     NNC_CHECK_LAUNCH();
-    k_g_rootT<<<(unsigned)ceil_div64(N * cin, 256), 256, sizeof(float) * cin * cout, st>>>(gout, root, N, cin, cout, dx);
+    k_g_rootT<<<(unsigned)ceil_div64(N * cin, 256), 256, sizeof(float) * cin * (cout + 1), st>>>(gout, root, N, cin, cout, dx);
     NNC_CHECK_LAUNCH();
   } else {
     NNC_CHECK_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * N * cin, st));
@@ -750,12 +759,11 @@ int backward_apply_tc(const Plan* P, const Weights* W, const void* h, const floa
   NNC_CHECK_LAUNCH();
   k_apply_scales<<<1, 1, 0, st>>>(scal);
   NNC_CHECK_LAUNCH();
-  if (bf) k_gather_g16<__nv_bfloat16><<<P->n_tiles, 256, 0, st>>>(gout, P->dst_sorted, inv_deg, P->tile_e0, P->tile_cnt, scal,
-                                                                  static_cast<__nv_bfloat16*>(G16));
-  else k_gather_g16<__half><<<P->n_tiles, 256, 0, st>>>(gout, P->dst_sorted, inv_deg, P->tile_e0, P->tile_cnt, scal,
-                                                        static_cast<__half*>(G16));
-  NNC_CHECK_LAUNCH();
-  k_group_gsum<<<ceil_div(S, 4), dim3(64, 4), 0, st>>>(gout, P->dst_sorted, inv_deg, P->group_ptr, S, cout, Gs);
+  NNC_CHECK_CUDA(cudaMemsetAsync(Gs, 0, sizeof(float) * static_cast<size_t>(S) * cout, st));
+  if (bf) k_gather_g16<__nv_bfloat16><<<P->n_tiles, 256, 0, st>>>(gout, P->dst_sorted, inv_deg, P->tile_c, P->tile_e0,
+                                                                  P->tile_cnt, scal, static_cast<__nv_bfloat16*>(G16), Gs);
+  else k_gather_g16<__half><<<P->n_tiles, 256, 0, st>>>(gout, P->dst_sorted, inv_deg, P->tile_c, P->tile_e0, P->tile_cnt, scal,
+                                                        static_cast<__half*>(G16), Gs);
   NNC_CHECK_LAUNCH();
   if (bf) k_prep_xg<__nv_bfloat16><<<(unsigned)ceil_div64(static_cast<int64_t>(S) * cin_p, 256), 256, 0, st>>>(
       x, P->src_nodes, S, cin, cin_p, scal, static_cast<__nv_bfloat16*>(Xg));
@@ -798,7 +806,7 @@ int backward_apply_tc(const Plan* P, const Weights* W, const void* h, const floa
     s = launch_gemm_tc(W->prec, dY, nb, 0, nb, NY, W->W3t, cin_p, nullptr, 0, dxp, cin_p, st, nullptr, 0, 0, 0, nullptr,
                        nullptr, 0, 1);
     if (s) return s;
-    k_scatter_dx_tc<<<(unsigned)ceil_div64(static_cast<int64_t>(nb) * cin, 256), 256, 0, st>>>(
+    k_scatter_dx_tc<<<(unsigned)ceil_div64(static_cast<int64_t>(nb) * cin, 256), 256, sizeof(float) * cin * (cout + 1), st>>>(
         dxp, cin_p, Gs, W->B3, P->src_nodes, static_cast<int>(c0), nb, cin, cout, scal, dx);
     NNC_CHECK_LAUNCH();
     // dW3[(k,o), i] += sum_c dY[c, (k,o)] Xg[c0 + c, i]

@@ -49,6 +49,7 @@ struct GemmTcArgs {
   int a_split_nk;
   int c_split;
   const float* acc_scale;     // optional device scalar multiplied into the fp32 accumulator before bias (exact power of two)
+  unsigned long long b_policy;   // L2 eviction hint of the B (weight) tiles
   int64_t a_chunk_rows_pad;   // > 0: A is chunk-major [K/64][a_chunk_rows_pad][64] (the edge-feature layout): K block kb of
                               // row r is the box at (0, kb * a_chunk_rows_pad + r) of the [K/64 * rows_pad, 64] view
   int* overflow;       // counts 32-column pieces holding a value beyond the fp16 range (fp16 outputs only), or nullptr
@@ -154,7 +155,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             tma_load_2d(smem_a + stage * Cfg::kABytes, &tmA, &full[stage], ka * Cfg::kBlockK,
                         a.a_row0 + mb * Cfg::kBlockM, kEvictNormal);
           tma_load_2d(smem_b + stage * Cfg::kBBytes, &tmB, &full[stage], kb * Cfg::kBlockK, nb * BLOCK_N,
-                      kEvictLast);
+                      a.b_policy);
         }
         __syncwarp();
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
@@ -424,6 +425,7 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
   a.chunk_rows_pad = chunk_rows_pad;
   a.c_row0 = c_row0;
   a.a_chunk_rows_pad = a_chunk_rows_pad;
+  a.b_policy = options().gemm_b_policy ? kEvictLast : kEvictNormal;
   a.acc_scale = acc_scale;
   a.a_split_nk = a_split ? K / 192 : 0;
   a.c_split = c_split ? 1 : 0;

@@ -23,6 +23,8 @@ const Entry kEntries[] = {
     {"debug_scatter", "NNCONV_DEBUG_SCATTER", &Options::debug_scatter, 0},
     {"y_store_policy", "NNCONV_Y_STORE_POLICY", &Options::y_store_policy, 0},
     {"l2_persist", "NNCONV_L2_PERSIST", &Options::l2_persist, 0},
+    {"l2_reset", "NNCONV_L2_RESET", &Options::l2_reset, 0},
+    {"gemm_b_policy", "NNCONV_GEMM_B_POLICY", &Options::gemm_b_policy, 1},
     {"conv_one_per_sm", "NNCONV_CONV_ONE_PER_SM", &Options::conv_one_per_sm, 0},
     {"conv_stages", "NNCONV_CONV_STAGES", &Options::conv_stages, 0},
     {"conv_debug", "NNCONV_DEBUG", &Options::conv_debug, 0},

@@ -12,7 +12,10 @@ struct Options {
   int apply_stages;       // NNCONV_APPLY_STAGES: cap on the A stages of the fused kernel (0 = no cap)
   int debug_scatter;      // NNCONV_DEBUG_SCATTER: timing experiments only (wrong results)
   int y_store_policy;     // NNCONV_Y_STORE_POLICY: 0 normal, 1 evict-last, 2 evict-first
-  int l2_persist;         // NNCONV_L2_PERSIST: access-policy window over the Y ring
+  int l2_persist;         // NNCONV_L2_PERSIST: access-policy window over the Y ring; value = persisting-L2 set-aside in MB
+                          // (1 = the device maximum)
+  int l2_reset;           // NNCONV_L2_RESET: cudaCtxResetPersistingL2Cache at the start of every edge-feature pass
+  int gemm_b_policy;      // NNCONV_GEMM_B_POLICY: L2 hint of the GEMM's B (weight) tiles: 1 evict-last (default), 0 normal
   int conv_one_per_sm;    // NNCONV_CONV_ONE_PER_SM
   int conv_stages;        // NNCONV_CONV_STAGES
   int conv_debug;         // NNCONV_DEBUG

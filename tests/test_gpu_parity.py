@@ -284,9 +284,10 @@ def test_low_out_degree_graph_uses_per_edge_kernel_matrices(dev, precision):
     ref = O.nnconv_forward(x, ei, ea, ws, bs, root, bias, 'mean')
     conv = make_conv(_conv_cls(), ws, bs, root, bias, 'mean', w, w, precision, dev)
     n0 = nn_conv.stats.get('edge_kernel_passes', 0)
+    xd, eid, ead = x.to(dev), ei.to(dev), ea.to(dev)
     with torch.no_grad():
-        out_b = conv(x.to(dev), ei.to(dev), ea.to(dev))
-        out_b2 = conv(2.0 * x.to(dev), ei.to(dev), ea.to(dev))       # second application reuses K_e
+        out_b = conv(xd, eid, ead)
+        out_b2 = conv(2.0 * xd, eid, ead)                            # second application reuses K_e
     assert nn_conv.stats.get('edge_kernel_passes', 0) == n0 + 1
     assert rel_err(out_b, ref) < TOL[precision]
     assert rel_err(out_b2 - bias.to(dev), 2.0 * (out_b - bias.to(dev))) < 1e-5
@@ -295,7 +296,7 @@ def test_low_out_degree_graph_uses_per_edge_kernel_matrices(dev, precision):
     try:
         conv_c = make_conv(_conv_cls(), ws, bs, root, bias, 'mean', w, w, precision, dev)
         with torch.no_grad():
-            out_c = conv_c(x.to(dev), ei.to(dev), ea.to(dev))
+            out_c = conv_c(xd, eid, ead)
     finally:
         nn_conv._EDGE_KERNELS = old
     assert rel_err(out_b, out_c) < 2 * TOL[precision]
