@@ -49,7 +49,9 @@ _BWD_MLP_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_MLP_WS_BYTES', str(6 << 
 _BWD_MODE = os.environ.get('NNCONV_B200_BACKWARD', 'auto')       # auto | tc | fp32
 # per-edge kernel matrices (formulation B) for graphs with few out-edges per source: auto | on | off
 _EDGE_KERNELS = os.environ.get('NNCONV_B200_EDGE_KERNELS', 'auto')
-_EDGE_KERNELS_MAX_DEG = 8                       # auto: average out-degree of the sources with out-edges
+_EDGE_KERNELS_MAX_DEG = 8                       # auto: average out-degree of the sources with out-edges ...
+_EDGE_KERNELS_MAX_EDGES = 16384                 # ... or a graph so small that streaming 8 KB per edge (<= 128 MB) costs less
+                                                # than the fixed cost of the persistent kernel (MGKN's coarse levels)
 _EDGE_KERNELS_MAX_BYTES = 2 << 30
 
 
@@ -436,7 +438,8 @@ class NNConv_old(torch.nn.Module):
         Cached with h: as x-independent as the edge features."""
         if _EDGE_KERNELS == 'off' or prepared.precision not in ('f16', 'fp16', 'bf16') or plan.E == 0:
             return None
-        if _EDGE_KERNELS != 'on' and not (plan.E <= _EDGE_KERNELS_MAX_DEG * max(plan.n_src, 1) and
+        if _EDGE_KERNELS != 'on' and not ((plan.E <= _EDGE_KERNELS_MAX_DEG * max(plan.n_src, 1) or
+                                           plan.E <= _EDGE_KERNELS_MAX_EDGES) and
                                           plan.E * self.in_channels * self.out_channels * 2 <= _EDGE_KERNELS_MAX_BYTES):
             return None
         hit = getattr(self, '_k_cache', None)

@@ -31,3 +31,15 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope='session')
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(params=['auto', 'off'])
+def edge_kernel_mode(request):
+    """Run a GPU test under both application paths: 'auto' (small / low out-degree graphs use per-edge kernel matrices,
+    formulation B) and 'off' (always the persistent fused kernel, formulation C) -- most test graphs are small enough
+    for 'auto' to pick B, and both paths must meet the same tolerances."""
+    from graph_pde_b200 import nn_conv
+    old = nn_conv._EDGE_KERNELS
+    nn_conv._EDGE_KERNELS = request.param
+    yield request.param
+    nn_conv._EDGE_KERNELS = old

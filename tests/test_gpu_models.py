@@ -10,7 +10,7 @@ import torch.nn.functional as F
 
 from tests.helpers import GOLDEN, TOL, cfg1_weights, ei64, rel_err, t
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures('edge_kernel_mode')]
 DEV = 'cuda:0'
 
 

@@ -9,7 +9,7 @@ import torch
 from oracle import nnconv_oracle as O
 from tests.helpers import GOLDEN, TOL, DenseNetLike, cfg1_weights, ei64, make_conv, rel_err, t
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures('edge_kernel_mode')]
 
 
 @pytest.fixture(scope='module')
@@ -270,11 +270,13 @@ def test_node_features_beyond_fp16_range(dev, precision, knob, lib_options):
 
 
 @pytest.mark.parametrize('precision', ['f16', 'bf16'])
-def test_low_out_degree_graph_uses_per_edge_kernel_matrices(dev, precision):
+def test_low_out_degree_graph_uses_per_edge_kernel_matrices(dev, precision, edge_kernel_mode):
     """The 1-D multipole stencils of MGKN_orthogonal_burgers1d.py give every node 2-4 out-edges: the conv switches
     to formulation B (K_e built once by the tcgen05 GEMM, one streaming pass per application) and must agree with
     the oracle and with formulation C on the same inputs."""
     from graph_pde_b200 import graphs, nn_conv
+    if edge_kernel_mode == 'off':
+        pytest.skip('this test switches the mode itself')
     s, w, kw = 512, 64, 128
     X, eis, eas = graphs.multi_pole_grid1d(torch.randn(s, generator=torch.Generator().manual_seed(0)), s, is_periodic=True,
                                            levels=3)
