@@ -224,8 +224,21 @@ size_t edge_features_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes
   return kEfHeader + rows * row + 8192;
 }
 
+size_t edge_acts_offset(const Plan* P, const Weights* W, int l) {
+  const size_t rows = static_cast<size_t>(round_up64(P->E > 0 ? P->E : 1, 128));
+  size_t off = 0;
+  for (int j = 1; j < l; ++j) off += rows * W->kp[j] * 2;
+  return off;
+}
+
+size_t edge_acts_bytes(const Plan* P, const Weights* W) {
+  if (W->split || W->prec == PREC_FP32 || W->n_layers < 3) return 0;
+  return edge_acts_offset(P, W, W->n_layers - 1) + 1024;
+}
+
 int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void* h, void* ws, size_t ws_bytes,
-                  cudaStream_t st, int64_t* launches) {
+                  cudaStream_t st, int64_t* launches, void* acts) {
+  if (acts != nullptr && edge_acts_bytes(P, W) == 0) acts = nullptr;
   const int64_t E = P->E;
   NNC_REQUIRE(ws != nullptr && ws_bytes >= kEfHeader, NNCONV_ERR_WORKSPACE, "edge_features: workspace too small");
   int* overflow = static_cast<int*>(ws);
@@ -273,7 +286,10 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
     const int64_t n = (E - e0) < rows ? (E - e0) : rows;
     void* h_rows = hpad > 0 ? h : static_cast<void*>(static_cast<char*>(h) + static_cast<size_t>(e0) * W->Kp * W->esize);
     const int64_t h_pad_l1 = nl == 2 ? hpad : 0;     // first layer writes h directly only for 2-layer MLPs
-    void* dst1 = nl == 2 ? h_rows : static_cast<void*>(bufA);
+    auto act_rows = [&](int l) -> char* {   // rows [e0, ...) of the kept activations of layer l
+      return static_cast<char*>(acts) + edge_acts_offset(P, W, l) + static_cast<size_t>(e0) * W->kp[l] * 2;
+    };
+    void* dst1 = nl == 2 ? h_rows : (acts ? static_cast<void*>(act_rows(1)) : static_cast<void*>(bufA));
     {
       ProfScope ps(PK_LAYER1, st);
       if (W->W1aug) {
@@ -290,10 +306,11 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
     }
     if (s) return s;
     if (launches) ++*launches;
-    char* cur = bufA;
+    char* cur = acts ? act_rows(1) : bufA;
     char* nxt = bufB;
     for (int l = 2; l <= nl - 1; ++l) {
       const bool last = l == nl - 1;
+      if (acts && !last) nxt = act_rows(l);
       void* dst = last ? h_rows : static_cast<void*>(nxt);
       ProfScope ps(PK_HIDDEN_GEMM, st);
       if (W->prec == PREC_FP32) {
@@ -308,7 +325,7 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
       }
       if (s) return s;
       if (launches) ++*launches;
-      char* tmp = cur; cur = nxt; nxt = tmp;
+      char* tmp = cur; cur = nxt; nxt = acts ? bufB : tmp;
     }
   }
   return NNCONV_OK;
@@ -667,6 +684,18 @@ int nnconv_edge_features(const nnconv_plan_t* plan, const nnconv_weights_t* w, c
   return edge_features(&plan->p, &w->w, edge_attr, h, ws, ws_bytes, static_cast<cudaStream_t>(stream), launches);
 }
 
+int nnconv_edge_acts_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t* bytes) {
+  NNC_REQUIRE(plan && w && bytes, NNCONV_ERR_ARG, "null pointer");
+  *bytes = edge_acts_bytes(&plan->p, &w->w);
+  return NNCONV_OK;
+}
+
+int nnconv_edge_features_keep(const nnconv_plan_t* plan, const nnconv_weights_t* w, const float* edge_attr, void* h,
+                              void* acts, void* ws, size_t ws_bytes, void* stream, int64_t* launches) {
+  NNC_REQUIRE(plan && w && (edge_attr || plan->p.E == 0) && h, NNCONV_ERR_ARG, "null pointer");
+  return edge_features(&plan->p, &w->w, edge_attr, h, ws, ws_bytes, static_cast<cudaStream_t>(stream), launches, acts);
+}
+
 int nnconv_edge_features_overflow(const void* ws, void* stream, int64_t* count) {
   NNC_REQUIRE(ws && count, NNCONV_ERR_ARG, "null pointer");
   int v = 0;
@@ -761,12 +790,12 @@ int nnconv_backward_mlp_sizes(const nnconv_plan_t* plan, const nnconv_weights_t*
 
 int nnconv_backward_mlp(const nnconv_plan_t* plan, const nnconv_weights_t* w, const float* edge_attr, const void* h,
                         int n_apps, const float* const* grad_out, const float* const* x, int aggr, float* const* grad_W,
-                        float* const* grad_b, void* ws, size_t ws_bytes, void* stream) {
+                        float* const* grad_b, void* ws, size_t ws_bytes, void* stream, const void* acts) {
   NNC_REQUIRE(plan && w && grad_out && x && grad_W && grad_b && ((edge_attr && h) || plan->p.E == 0), NNCONV_ERR_ARG,
               "null pointer");
   NNC_REQUIRE(aggr == NNCONV_AGGR_ADD || aggr == NNCONV_AGGR_MEAN, NNCONV_ERR_UNSUPPORTED, "aggr must be add or mean");
   return backward_mlp_tc(&plan->p, &w->w, edge_attr, h, n_apps, grad_out, x, aggr == NNCONV_AGGR_MEAN, grad_W, grad_b, ws,
-                         ws_bytes, static_cast<cudaStream_t>(stream));
+                         ws_bytes, static_cast<cudaStream_t>(stream), acts);
 }
 
 int nnconv_gemm_tn_16b(int precision, const void* A, int64_t lda, const void* B, int64_t ldb, int64_t R, int M, int N,

@@ -868,8 +868,9 @@ size_t backward_mlp_ws_bytes(const Plan* P, const Weights* W, int T, size_t want
 
 int backward_mlp_tc(const Plan* P, const Weights* W, const float* edge_attr, const void* h, int T,
                     const float* const* gouts, const float* const* xs_in, int aggr_mean, float* const* dWs,
-                    float* const* dbs, void* ws, size_t ws_bytes, cudaStream_t st) {
+                    float* const* dbs, void* ws, size_t ws_bytes, cudaStream_t st, const void* acts) {
   NNC_REQUIRE(backward_tc_supported(W), NNCONV_ERR_UNSUPPORTED, "tensor-core backward: unsupported shape / precision");
+  if (acts != nullptr && edge_acts_bytes(P, W) == 0) acts = nullptr;
   NNC_REQUIRE(T >= 1 && T <= kMaxApps, NNCONV_ERR_ARG, "backward_mlp: 1..%d applications per pass", kMaxApps);
   const int nl = W->n_layers;
   const int cin = W->cin, cout = W->cout, Kp = W->Kp, cin_p = W->cin_p, k_in = W->dims[0];
@@ -947,7 +948,13 @@ int backward_mlp_tc(const Plan* P, const Weights* W, const float* edge_attr, con
     uint16_t* dzB = cv.take<uint16_t>(static_cast<size_t>(n_pad) * maxkp);
     uint16_t* A1 = cv.take<uint16_t>(static_cast<size_t>(n_pad) * 64);
     uint16_t* act[kMaxLayers + 1] = {nullptr};
-    for (int l = 1; l <= nl - 2; ++l) act[l] = cv.take<uint16_t>(static_cast<size_t>(n_pad) * W->kp[l]);
+    for (int l = 1; l <= nl - 2; ++l) {
+      if (acts != nullptr)   // kept by the forward (nnconv_edge_features_keep): rows [e_base, e_base + n) of layer l
+        act[l] = const_cast<uint16_t*>(reinterpret_cast<const uint16_t*>(static_cast<const char*>(acts) + edge_acts_offset(P, W, l))) +
+                 static_cast<size_t>(e_base) * W->kp[l];
+      else
+        act[l] = cv.take<uint16_t>(static_cast<size_t>(n_pad) * W->kp[l]);
+    }
     NNC_REQUIRE(cv.ok(), NNCONV_ERR_WORKSPACE, "backward_mlp: workspace carve overflow");
     // ---- Y^T of the batch for every application: Yt[t][(c, k), o] = sum_i Xc_t[c, i] W_L[i*out + o, k]
     for (int t = 0; t < T; ++t) {
@@ -988,7 +995,7 @@ int backward_mlp_tc(const Plan* P, const Weights* W, const float* edge_attr, con
     // ---- recompute the hidden activations h_1 .. h_{L-2} of the batch (16-bit, row-major) and A1
     s = launch_build_a1(W->prec, edge_attr, P->perm, e_base, n, k_in, A1, st);
     if (s) return s;
-    if (nl >= 3) {
+    if (nl >= 3 && acts == nullptr) {
       s = launch_gemm_tc(W->prec, A1, n, 0, n, 64, W->W1aug, W->kp[1], nullptr, 1, act[1], W->kp[1], st);
       if (s) return s;
       for (int l = 2; l <= nl - 2; ++l) {

@@ -79,8 +79,12 @@ int weights_prepare(Weights* W, int n_layers, const int* dims, int cin, int cout
 
 // edge features: h_last[p, :] for every sorted edge p  (x-independent prefix of the edge MLP)
 size_t edge_features_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes);
+// acts (nullable, training): keeps the hidden activations h_1 .. h_{L-2} of ALL edges (16-bit row-major, layer l at
+// edge_acts_offset(l)) instead of recycling them chunk by chunk, so that the backward need not recompute them
+size_t edge_acts_bytes(const Plan* P, const Weights* W);
+size_t edge_acts_offset(const Plan* P, const Weights* W, int l);
 int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void* h, void* ws, size_t ws_bytes,
-                  cudaStream_t st, int64_t* launches);
+                  cudaStream_t st, int64_t* launches, void* acts = nullptr);
 
 // one conv application given h_last
 size_t apply_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes);
@@ -97,7 +101,7 @@ int backward_apply_tc(const Plan* P, const Weights* W, const void* h, const floa
 size_t backward_mlp_ws_bytes(const Plan* P, const Weights* W, int T, size_t want_bytes);
 int backward_mlp_tc(const Plan* P, const Weights* W, const float* edge_attr, const void* h, int T,
                     const float* const* gouts, const float* const* xs_in, int aggr_mean, float* const* dWs,
-                    float* const* dbs, void* ws, size_t ws_bytes, cudaStream_t st);
+                    float* const* dbs, void* ws, size_t ws_bytes, cudaStream_t st, const void* acts = nullptr);
 
 // per-edge kernel matrices for low out-degree graphs (formulation B): Kmat [E, cin*cout] 16-bit in sorted edge order
 size_t edge_kernels_bytes(const Plan* P, const Weights* W);

@@ -47,6 +47,9 @@ _BWD_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_WS_BYTES', str(2 << 30)))  #
 _BWD_APPLY_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_APPLY_WS_BYTES', str(9 << 30)))
 _BWD_MLP_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_MLP_WS_BYTES', str(6 << 30)))
 _BWD_MODE = os.environ.get('NNCONV_B200_BACKWARD', 'auto')       # auto | tc | fp32
+# training: keep the hidden activations h_1..h_{L-2} of the forward for the backward (2 KB per edge and layer at width
+# 1024: 50 GB at 241^2) instead of recomputing them, when they fit this budget
+_KEEP_ACTS_MAX_BYTES = int(os.environ.get('NNCONV_B200_KEEP_ACTS_BYTES', str(64 << 30)))
 # per-edge kernel matrices (formulation B) for graphs with few out-edges per source: auto | on | off
 _EDGE_KERNELS = os.environ.get('NNCONV_B200_EDGE_KERNELS', 'auto')
 _EDGE_KERNELS_MAX_DEG = 8                       # auto: average out-degree of the sources with out-edges ...
@@ -222,6 +225,7 @@ class _TrainState(object):
         self.apps = []
         self.consumed = False
         self.token = None
+        self.acts = None            # hidden activations kept by the forward (nnconv_edge_features_keep), or None
 
 
 class _EdgeFeaturesFn(torch.autograd.Function):
@@ -241,7 +245,7 @@ class _EdgeFeaturesFn(torch.autograd.Function):
         grads = ctx.module._backward_mlp_impl(state)
         state.consumed = True
         state.apps = []
-        state.h = state.ea32 = None          # the 2 KB/edge features are no longer pinned by this (finished) graph
+        state.h = state.ea32 = state.acts = None     # the per-edge buffers are no longer pinned by this (finished) graph
         return (None, None) + tuple(grads)
 
 
@@ -377,13 +381,19 @@ class NNConv_old(torch.nn.Module):
             self._k_cache = None
         return self._prepared
 
-    def edge_features(self, plan, prepared, edge_attr):
-        """x-independent part of message(): cached across the T applications of a shared conv."""
+    def edge_features(self, plan, prepared, edge_attr, keep_acts=False):
+        """x-independent part of message(): cached across the T applications of a shared conv.  keep_acts (training):
+        also keep the hidden activations for the backward (returned by ``kept_acts``)."""
         key = (plan.key, edge_attr.data_ptr(), tuple(edge_attr.shape), edge_attr._version, id(prepared))
         hit = self._h_cache.get(key)
-        if hit is not None:
-            return hit[0]
         L = _lib.lib()
+        acts_b = ctypes.c_size_t(0)
+        if keep_acts:
+            _lib.check(L.nnconv_edge_acts_sizes(plan.handle, prepared.handle, ctypes.byref(acts_b)))
+            if acts_b.value > _KEEP_ACTS_MAX_BYTES:
+                acts_b = ctypes.c_size_t(0)
+        if hit is not None and (acts_b.value == 0 or hit[2] is not None):
+            return hit[0]
         h_b, ws_b = ctypes.c_size_t(), ctypes.c_size_t()
         _lib.check(L.nnconv_edge_features_sizes(plan.handle, prepared.handle, _EF_WS_BYTES, ctypes.byref(h_b),
                                                 ctypes.byref(ws_b)))
@@ -392,9 +402,14 @@ class NNConv_old(torch.nn.Module):
         self._k_cache = None
         h = torch.empty(h_b.value, dtype=torch.uint8, device=dev)
         ws = torch.empty(ws_b.value, dtype=torch.uint8, device=dev)
+        acts = torch.empty(acts_b.value, dtype=torch.uint8, device=dev) if acts_b.value else None
         n_l = ctypes.c_int64(0)
-        _lib.check(L.nnconv_edge_features(plan.handle, prepared.handle, _ptr(edge_attr), _ptr(h), _ptr(ws),
-                                          ws_b.value, _stream_ptr(dev), ctypes.byref(n_l)))
+        if acts is not None:
+            _lib.check(L.nnconv_edge_features_keep(plan.handle, prepared.handle, _ptr(edge_attr), _ptr(h), _ptr(acts),
+                                                   _ptr(ws), ws_b.value, _stream_ptr(dev), ctypes.byref(n_l)))
+        else:
+            _lib.check(L.nnconv_edge_features(plan.handle, prepared.handle, _ptr(edge_attr), _ptr(h), _ptr(ws),
+                                              ws_b.value, _stream_ptr(dev), ctypes.byref(n_l)))
         stats['launches'] += n_l.value
         stats['edge_feature_passes'] += 1
         if _OVERFLOW_CHECK and prepared.precision in ('f16', 'fp16', 'f16x2') and \
@@ -406,8 +421,14 @@ class NNConv_old(torch.nn.Module):
                     'graph_pde_b200.NNConv: %d blocks of edge-MLP activations left the fp16 range (|h| > 65504 or '
                     "NaN); use precision='bf16' or 'fp32' for this parameter scale (NNCONV_B200_OVERFLOW_CHECK=0 "
                     'disables this check and its one host sync per edge-feature pass)' % cnt.value)
-        self._h_cache[key] = (h, edge_attr)          # hold edge_attr so its address cannot be recycled
+        self._h_cache[key] = (h, edge_attr, acts)    # hold edge_attr so its address cannot be recycled
         return h
+
+    def kept_acts(self, h):
+        for ent in self._h_cache.values():
+            if ent[0] is h:
+                return ent[2]
+        return None
 
     def _check_inputs(self, x, edge_index, pseudo):
         _require_cuda(x, 'x')
@@ -422,7 +443,7 @@ class NNConv_old(torch.nn.Module):
         if pseudo.size(0) != edge_index.size(1):
             raise ValueError('edge_attr has %d rows for %d edges' % (pseudo.size(0), edge_index.size(1)))
 
-    def _prepare(self, x, edge_index, pseudo):
+    def _prepare(self, x, edge_index, pseudo, keep_acts=False):
         """plan, prepared weights, fp32 edge_attr and the (cached) edge features for this call."""
         precision = self.precision or default_precision()
         ea32 = pseudo.detach()
@@ -430,7 +451,7 @@ class NNConv_old(torch.nn.Module):
             ea32 = ea32.contiguous().float()
         plan = get_plan(edge_index, x.size(0), self.flow)
         prepared = self._get_prepared(precision)
-        h = self.edge_features(plan, prepared, ea32)
+        h = self.edge_features(plan, prepared, ea32, keep_acts and prepared.bwd_tc)
         return plan, prepared, ea32, h
 
     def _edge_kernels(self, plan, prepared, h):
@@ -499,7 +520,7 @@ class NNConv_old(torch.nn.Module):
             return None
         self._check_inputs(x, edge_index, pseudo)
         with torch.cuda.device(x.device):
-            plan, prepared, ea32, h = self._prepare(x, edge_index, pseudo)
+            plan, prepared, ea32, h = self._prepare(x, edge_index, pseudo, keep_acts=True)
             if not prepared.bwd_tc:
                 if mode == 'tc':
                     raise NotImplementedError('NNCONV_B200_BACKWARD=tc: shape / precision not covered by the tensor-core backward')
@@ -508,6 +529,7 @@ class NNConv_old(torch.nn.Module):
             st = getattr(self, '_tstate', None)
             if st is None or st.key != key or st.consumed or st.h is not h:
                 st = _TrainState(key, plan, prepared, h, ea32)
+                st.acts = self.kept_acts(h)
                 hidden = []
                 for l in _linear_chain(self.nn)[:-1]:
                     hidden += [l.weight, l.bias]
@@ -558,7 +580,8 @@ class NNConv_old(torch.nn.Module):
                 wp = (ctypes.c_void_p * len(hidden))(*[t.data_ptr() for t in dws])
                 bp = (ctypes.c_void_p * len(hidden))(*[t.data_ptr() for t in dbs])
                 _lib.check(L.nnconv_backward_mlp(plan.handle, prep.handle, _ptr(state.ea32), _ptr(state.h), n, gp, xp,
-                                                 _lib.AGGR[self.aggr], wp, bp, _ptr(ws), ws_b.value, _stream_ptr(dev)))
+                                                 _lib.AGGR[self.aggr], wp, bp, _ptr(ws), ws_b.value, _stream_ptr(dev),
+                                                 _ptr(getattr(state, 'acts', None))))
                 flat = [t for pair in zip(dws, dbs) for t in pair]
                 total = flat if total is None else [a + b for a, b in zip(total, flat)]
             stats['mlp_backwards'] = stats.get('mlp_backwards', 0) + 1

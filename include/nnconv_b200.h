@@ -109,6 +109,13 @@ int nnconv_edge_features_sizes(const nnconv_plan_t* plan, const nnconv_weights_t
 int nnconv_edge_features(const nnconv_plan_t* plan, const nnconv_weights_t* w, const float* edge_attr /*[E,k_in]*/,
                          void* h, void* ws, size_t ws_bytes, void* stream, int64_t* launches /*nullable*/);
 
+/* Training variant: additionally KEEPS the hidden activations h_1 .. h_{L-2} of every edge in `acts`
+ * (nnconv_edge_acts_sizes bytes; 0 = nothing to keep for this configuration, pass NULL) so that
+ * nnconv_backward_mlp need not recompute them (2 KB per edge and kept layer at width 1024). */
+int nnconv_edge_acts_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t* bytes);
+int nnconv_edge_features_keep(const nnconv_plan_t* plan, const nnconv_weights_t* w, const float* edge_attr, void* h,
+                              void* acts, void* ws, size_t ws_bytes, void* stream, int64_t* launches /*nullable*/);
+
 /* Number of 32-column output pieces of the LAST nnconv_edge_features call on `ws` that left the fp16 range
  * (|v| > 65504 or NaN; fp16 precisions only, always 0 for bf16 / fp32 or with option overflow_check = 0).
  * Copies one int to the host and synchronises `stream`.  A non-zero count means h holds inf: use bf16 / fp32. */
@@ -163,7 +170,8 @@ int nnconv_backward_mlp_sizes(const nnconv_plan_t* plan, const nnconv_weights_t*
                               size_t* ws_bytes);
 int nnconv_backward_mlp(const nnconv_plan_t* plan, const nnconv_weights_t* w, const float* edge_attr, const void* h,
                         int n_apps, const float* const* grad_out, const float* const* x, int aggr, float* const* grad_W,
-                        float* const* grad_b, void* ws, size_t ws_bytes, void* stream);
+                        float* const* grad_b, void* ws, size_t ws_bytes, void* stream,
+                        const void* acts /* from nnconv_edge_features_keep, or NULL = recompute */);
 
 /* ---- halo exchange of the node-range (strip) partition by peer stores over NVLink (no NCCL call, no host round
  * trip between applications).  `out` [n_local, channels] is the result of one application on this rank (owned rows
