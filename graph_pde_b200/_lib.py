@@ -27,7 +27,7 @@ SYMBOLS = [
     'nnconv_set_option', 'nnconv_get_option', 'nnconv_edge_features_overflow', 'nnconv_debug_occupy',
     'nnconv_backward_tc_supported', 'nnconv_backward_apply_sizes', 'nnconv_backward_apply',
     'nnconv_backward_mlp_sizes', 'nnconv_backward_mlp', 'nnconv_gemm_tn_16b', 'nnconv_gemm_16b_ex',
-    'nnconv_halo_push', 'nnconv_halo_wait', 'nnconv_loss_epilogue',
+    'nnconv_halo_push', 'nnconv_halo_wait', 'nnconv_enable_peer_access', 'nnconv_loss_epilogue',
     'nnconv_ball_count', 'nnconv_ball_fill',
     'nnconv_edge_kernels_sizes', 'nnconv_edge_kernels', 'nnconv_apply_edge',
     'nnconv_edge_acts_sizes', 'nnconv_edge_features_keep',
@@ -104,6 +104,7 @@ def lib():
     L.nnconv_halo_push.argtypes = [c_vp, c_int, c_i64, c_int, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64,
                                    c_i64, c_i64, c_vp, c_vp, c_int, c_vp]
     L.nnconv_halo_wait.argtypes = [c_vp, c_vp, c_int, c_vp]
+    L.nnconv_enable_peer_access.argtypes = [c_int]
     L.nnconv_edge_kernels_sizes.argtypes = [c_vp, c_vp, P(c_sz)]
     L.nnconv_edge_kernels.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp]
     L.nnconv_apply_edge.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]

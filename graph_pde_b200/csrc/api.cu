@@ -819,6 +819,19 @@ int nnconv_halo_push(const float* out, int relu, int64_t n_local, int channels, 
                    dn_src0, dn_dst0, dn_rows, flag_up, flag_down, seq, static_cast<cudaStream_t>(stream));
 }
 
+int nnconv_enable_peer_access(int peer_device) {
+  int dev = 0;
+  NNC_CHECK_CUDA(cudaGetDevice(&dev));
+  if (peer_device == dev) return NNCONV_OK;
+  int can = 0;
+  NNC_CHECK_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+  NNC_REQUIRE(can, NNCONV_ERR_UNSUPPORTED, "device %d cannot access device %d (no P2P path)", dev, peer_device);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+  NNC_CHECK_CUDA(e);
+  return NNCONV_OK;
+}
+
 int nnconv_halo_wait(const int* flag_from_up, const int* flag_from_down, int seq, void* stream) {
   return halo_wait(flag_from_up, flag_from_down, seq, static_cast<cudaStream_t>(stream));
 }

@@ -171,8 +171,10 @@ class PeerHalo(object):
         self._keep = []
 
         def open_(r):
-            ts = [fn(*args) for fn, args in gathered[r]]
+            ts = [fn(*args) for fn, args in gathered[r]]       # tensors on the NEIGHBOUR's device, mapped by CUDA IPC
             self._keep.append(ts)
+            with torch.cuda.device(device):                    # this rank's kernels will store into them
+                _lib.check(self.L.nnconv_enable_peer_access(ts[0].device.index))
             return ts
         self.up = open_(part.rank - 1) if part.rank > 0 else None
         self.down = open_(part.rank + 1) if part.rank < part.world - 1 else None

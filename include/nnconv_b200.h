@@ -184,6 +184,9 @@ int nnconv_halo_push(const float* out, int relu, int64_t n_local, int channels, 
                      int64_t dn_src0, int64_t dn_dst0, int64_t dn_rows, int* flag_up, int* flag_down, int seq,
                      void* stream);
 int nnconv_halo_wait(const int* flag_from_up, const int* flag_from_down, int seq, void* stream);
+/* kernels of the CURRENT device may load / store memory of `peer_device` afterwards (cudaDeviceEnablePeerAccess;
+ * needed once per neighbour before nnconv_halo_push writes into its IPC-mapped buffers) */
+int nnconv_enable_peer_access(int peer_device);
 
 /* ---- ball-graph construction on the device (replaces np.where(pairwise_distances(pa, pb) <= r), utilities.py:250-255
  * and multipole utilities.py:602-643, plus the attribute gather :269-285 / :672-706), two passes:

@@ -239,3 +239,33 @@ def test_tc_backward_config2_size():
     print('config-2-size gradient errors vs mask-consistent fp32 autograd:', errs)
     bad = {k: v for k, v in errs.items() if not v < 5e-3}
     assert not bad, (bad, errs)
+
+
+def test_kept_and_recomputed_hidden_activations_give_the_same_gradients(monkeypatch):
+    """Training keeps h_1..h_{L-2} of the forward when they fit NNCONV_B200_KEEP_ACTS_BYTES, else the deferred pass
+    recomputes them per batch: same gradients either way (4-layer MLP: two kept layers)."""
+    from graph_pde_b200 import nn_conv
+    from graph_pde_b200.nn_conv import NNConv_old
+    gen = torch.Generator().manual_seed(23)
+    N, E, w = 200, 6000, 64
+    ei = _graph(gen, N, E, hub=True)
+    ea = torch.randn(E, 6, generator=gen)
+    x = torch.randn(N, w, generator=gen)
+    gout = torch.randn(N, w, generator=gen)
+    torch.manual_seed(4)
+    mlp = DenseNetLike([6, 128, 64, 192, w * w])
+    lin = [m for m in mlp.layers if isinstance(m, torch.nn.Linear)]
+    ws, bs = [l.weight.detach().clone() for l in lin], [l.bias.detach().clone() for l in lin]
+    grads = []
+    for budget in (64 << 30, 0):
+        monkeypatch.setattr(nn_conv, '_KEEP_ACTS_MAX_BYTES', budget)
+        conv = make_conv(NNConv_old, ws, bs, torch.randn(w, w) * 0.1, None, 'mean', w, w, 'f16', DEV)
+        xd = x.to(DEV).requires_grad_(True)
+        h = torch.relu(conv(xd, ei.to(DEV), ea.to(DEV)))
+        kept = conv._tstate.acts is not None
+        assert kept == (budget > 0)
+        (h * gout.to(DEV)).sum().backward()
+        lin_d = [m for m in conv.nn.layers if isinstance(m, torch.nn.Linear)]
+        grads.append([xd.grad] + [l.weight.grad for l in lin_d] + [l.bias.grad for l in lin_d])
+    for a, b in zip(*grads):
+        assert _relerr(a, b) < 1e-5
