@@ -349,6 +349,112 @@ def other_configs(dev, precision):
     return out
 
 
+def strip_child_main(args):
+    """`bench.py --strip-only` (spawned by every rank of the main bench, own process group): ONE mesh cut into N row
+    strips (strong scaling; SURVEY 8(e) "single big mesh").  Every rank owns the edges that END in its strip, computes
+    their edge features, and the T applications exchange 2R boundary rows with the two neighbours by peer stores over
+    NVLink (partition.PeerHalo, csrc/halo.cu) -- inside the timed region.  Runs in child processes so that a failure
+    of the peer mapping on some box cannot take the headline line down with it.  Rank 0 prints one JSON object."""
+    import torch.distributed as dist
+    from graph_pde_b200 import graphs, partition
+    from graph_pde_b200.models import KernelNN
+    cfg = WORKLOADS[args.workload]
+    rank, world, local_rank = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist.init_process_group('nccl', device_id=dev)
+    s, r, w, kw, T = cfg['s'], cfg['r'], cfg['width'], cfg['ker_width'], cfg['depth']
+    torch.manual_seed(0)
+    model = KernelNN(w, kw, T, 6, in_width=6, precision=args.precision).to(dev).eval()
+    ei = graphs.ball_connectivity(s, r, dev, True)
+    E = ei.size(1)
+    x6c, _, _ = graphs.darcy_sample(s, r, dev, seed=4242, edge_index=ei[:, :1])     # the SAME sample on every rank
+    part = partition.StripPartition(s, r, rank, world, device=dev)
+    grid = graphs.square_grid(s, dev)
+    ea_loc = graphs.ball_edge_attr(grid, part.edge_index_global, x6c[:, 2])
+    with torch.no_grad():
+        x0g = model.fc1(x6c)
+    x_loc = part.local_slice(x0g).clone()
+    mode = 'peer stores + flags (CUDA IPC over NVLink)'
+    try:
+        halo = partition.PeerHalo(part, w, dev)
+    except Exception as exc:                                   # e.g. IPC not permitted in this container
+        halo = None
+        mode = 'NCCL all-gather per application (peer mapping failed: %s)' % type(exc).__name__
+    ok_all = torch.tensor([1 if halo is not None else 0], device=dev)
+    dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
+    if int(ok_all.item()) == 0 and halo is not None:
+        halo, mode = None, 'NCCL all-gather per application (peer mapping failed on another rank)'
+    conv_fn = lambda xl, e, a: model.conv1(xl, e, a)          # noqa: E731
+
+    def step_strip(i):
+        model.conv1._h_cache.clear()
+        with torch.no_grad():
+            if halo is not None:
+                return partition.partitioned_conv_stack_peer(conv_fn, x_loc, part, ea_loc, T, halo)
+            return partition.partitioned_conv_stack(conv_fn, x_loc.clone(), part, ea_loc, T)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+    ssteps = max(2, min(args.steps, 5))
+    for i in range(3):
+        step_strip(i)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(ssteps):
+        step_strip(i)
+    b.record()
+    barrier()
+    ms = torch.tensor([a.elapsed_time(b)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_strip = float(ms.item())
+    got = step_strip(0)
+    # parity against the unpartitioned stack on the same sample (every rank computes it: 1 step)
+    model.conv1._h_cache.clear()
+    torch.cuda.empty_cache()
+    with torch.no_grad():
+        ea_full = graphs.ball_edge_attr(grid, ei, x6c[:, 2])
+        full = model.conv_stack(x0g, ei, ea_full)
+    ref = full[part.row_lo * s:part.row_hi * s]
+    err = torch.tensor([float((got - ref).abs().max() / ref.abs().max())], device=dev)
+    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+    halo_bytes = 2 * part.R * s * w * 4 * (T - 1)
+    if rank == 0:
+        print(json.dumps(dict(
+            value=E * T * ssteps / (ms_strip * 1e-3), unit='edge-apps/s', scaling='strong', ms_per_step=ms_strip / ssteps,
+            steps=ssteps, n_gpus=world, halo=mode, nvlink_bytes_per_rank_per_step=halo_bytes,
+            local_edges=int(part.edge_index.size(1)), parity_vs_unpartitioned=float(err.item()),
+            note='one %dx%d mesh (E=%d) cut into %d row strips, edges owned by their destination; a step = edge features '
+                 'of the local edges + T applications with a halo push after each; timed with CUDA events, max over '
+                 'ranks' % (s, s, E, world))))
+    if halo is not None:
+        halo.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0
+
+
+def run_strip_children(args, rank):
+    """Every rank of the main bench spawns its own child (same RANK / WORLD_SIZE / LOCAL_RANK, MASTER_PORT + 23);
+    rank 0 returns the child's JSON object (or an error record)."""
+    env = dict(os.environ)
+    env['MASTER_PORT'] = str(int(env.get('MASTER_PORT', '29500')) + 23)
+    cmd = [sys.executable, os.path.abspath(__file__), '--strip-only', '--workload', args.workload, '--precision',
+           args.precision, '--steps', str(args.steps)]
+    try:
+        res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=420)
+        if rank != 0:
+            return None
+        lines = [l for l in res.stdout.splitlines() if l.startswith('{')]
+        if res.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        return dict(error='strip child rc=%d: %s' % (res.returncode, res.stderr.strip().splitlines()[-1][:300] if res.stderr.strip() else ''))
+    except subprocess.TimeoutExpired:
+        return dict(error='strip child timed out') if rank == 0 else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -362,7 +468,10 @@ def main():
     ap.add_argument('--no-train', action='store_true', help='skip the training-step measurement')
     ap.add_argument('--no-other-configs', action='store_true', help='skip BASELINE configs 2, 4, 5')
     ap.add_argument('--no-strip', action='store_true', help='skip the single-mesh strip-partition measurement (N > 1)')
+    ap.add_argument('--strip-only', action='store_true', help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.strip_only:
+        return strip_child_main(args)
     cfg = WORKLOADS[args.workload]
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -546,62 +655,6 @@ def main():
         torch.cuda.empty_cache()
     barrier()
 
-    # ---- ONE mesh cut into N row strips (strong scaling; SURVEY 8(e) "single big mesh"): every rank owns the edges
-    # that END in its strip, computes their edge features, and the T applications exchange 2R boundary rows with the
-    # two neighbours by peer stores over NVLink (partition.PeerHalo, csrc/halo.cu) -- inside the timed region.
-    strip = None
-    if world > 1 and not args.no_strip:
-        from graph_pde_b200 import partition
-        model.conv1._h_cache.clear()
-        torch.cuda.empty_cache()
-        x6c, _, _ = graphs.darcy_sample(s, r, dev, seed=4242, edge_index=ei[:, :1])     # the SAME sample on every rank
-        part = partition.StripPartition(s, r, rank, world, device=dev)
-        grid = graphs.square_grid(s, dev)
-        ea_loc = graphs.ball_edge_attr(grid, part.edge_index_global, x6c[:, 2])
-        with torch.no_grad():
-            x0g = model.fc1(x6c)
-        x_loc = part.local_slice(x0g).clone()
-        mode = 'peer stores + flags (CUDA IPC over NVLink)'
-        try:
-            halo = partition.PeerHalo(part, w, dev)
-        except Exception as exc:                                   # e.g. IPC not permitted in this container
-            halo = None
-            mode = 'NCCL all-gather per application (peer mapping failed: %s)' % type(exc).__name__
-        ok_all = torch.tensor([1 if halo is not None else 0], device=dev)
-        dist.all_reduce(ok_all, op=dist.ReduceOp.MIN)
-        if int(ok_all.item()) == 0 and halo is not None:
-            halo, mode = None, 'NCCL all-gather per application (peer mapping failed on another rank)'
-        conv_fn = lambda xl, e, a: model.conv1(xl, e, a)          # noqa: E731
-
-        def step_strip(i):
-            model.conv1._h_cache.clear()
-            with torch.no_grad():
-                if halo is not None:
-                    return partition.partitioned_conv_stack_peer(conv_fn, x_loc, part, ea_loc, T, halo)
-                return partition.partitioned_conv_stack(conv_fn, x_loc.clone(), part, ea_loc, T)
-        ssteps = max(2, min(args.steps, 5))
-        ms_strip = timed(step_strip, ssteps, 3)
-        got = step_strip(0)
-        # parity against the unpartitioned stack on the same sample (every rank computes it: 1 step)
-        model.conv1._h_cache.clear()
-        torch.cuda.empty_cache()
-        with torch.no_grad():
-            ea_full = graphs.ball_edge_attr(grid, ei, x6c[:, 2])
-            full = model.conv_stack(x0g, ei, ea_full)
-        ref = full[part.row_lo * s:part.row_hi * s]
-        err = torch.tensor([float((got - ref).abs().max() / ref.abs().max())], device=dev)
-        dist.all_reduce(err, op=dist.ReduceOp.MAX)
-        halo_bytes = 2 * part.R * s * w * 4 * (T - 1)
-        strip = dict(value=E * T * ssteps / (ms_strip * 1e-3), unit='edge-apps/s', scaling='strong', ms_per_step=ms_strip / ssteps,
-                     steps=ssteps, n_gpus=world, halo=mode, nvlink_bytes_per_rank_per_step=halo_bytes,
-                     local_edges=int(part.edge_index.size(1)), parity_vs_unpartitioned=float(err.item()),
-                     note='one %dx%d mesh (E=%d) cut into %d row strips, edges owned by their destination; a step = edge '
-                          'features of the local edges + T applications with a halo push after each' % (s, s, E, world))
-        del full, ea_full, got, halo
-        model.conv1._h_cache.clear()
-        torch.cuda.empty_cache()
-    barrier()
-
     # ---- parity at the benchmarked configuration and precision + the fp32-grade (f16x2) line, rank 0 only
     parity, fp32_grade = None, None
     if rank == 0 and not args.no_parity:
@@ -656,6 +709,15 @@ def main():
         except Exception as exc:           # never lose the headline line to a secondary measurement
             configs = dict(error='%s: %s' % (type(exc).__name__, str(exc)[:300]))
     barrier()
+
+    # ---- ONE mesh cut into N row strips (strong scaling), in child processes: see strip_child_main
+    strip = None
+    if world > 1 and not args.no_strip:
+        model.conv1._h_cache.clear()
+        nn_conv.clear_caches()
+        torch.cuda.empty_cache()
+        strip = run_strip_children(args, rank)
+        barrier()
 
     if rank == 0:
         pk = peaks()

@@ -28,6 +28,7 @@ SYMBOLS = [
     'nnconv_backward_tc_supported', 'nnconv_backward_apply_sizes', 'nnconv_backward_apply',
     'nnconv_backward_mlp_sizes', 'nnconv_backward_mlp', 'nnconv_gemm_tn_16b', 'nnconv_gemm_16b_ex',
     'nnconv_halo_push', 'nnconv_halo_wait', 'nnconv_enable_peer_access', 'nnconv_loss_epilogue',
+    'nnconv_ipc_alloc', 'nnconv_ipc_open', 'nnconv_ipc_close', 'nnconv_ipc_free',
     'nnconv_ball_count', 'nnconv_ball_fill',
     'nnconv_edge_kernels_sizes', 'nnconv_edge_kernels', 'nnconv_apply_edge',
     'nnconv_edge_acts_sizes', 'nnconv_edge_features_keep',
@@ -105,6 +106,10 @@ def lib():
                                    c_i64, c_i64, c_vp, c_vp, c_int, c_vp]
     L.nnconv_halo_wait.argtypes = [c_vp, c_vp, c_int, c_vp]
     L.nnconv_enable_peer_access.argtypes = [c_int]
+    L.nnconv_ipc_alloc.argtypes = [c_sz, P(c_vp), ctypes.c_char_p]
+    L.nnconv_ipc_open.argtypes = [ctypes.c_char_p, P(c_vp)]
+    L.nnconv_ipc_close.argtypes = [c_vp]
+    L.nnconv_ipc_free.argtypes = [c_vp]
     L.nnconv_edge_kernels_sizes.argtypes = [c_vp, c_vp, P(c_sz)]
     L.nnconv_edge_kernels.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp]
     L.nnconv_apply_edge.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]

@@ -819,6 +819,46 @@ int nnconv_halo_push(const float* out, int relu, int64_t n_local, int channels, 
                    dn_src0, dn_dst0, dn_rows, flag_up, flag_down, seq, static_cast<cudaStream_t>(stream));
 }
 
+// Peer-visible buffers of the halo exchange.  They are the one place (besides the optional trace buffer) where the
+// library allocates device memory itself: a CUDA IPC handle can only be taken of a whole cudaMalloc allocation, and
+// the importing side must open it with ITS device current (cudaIpcMemLazyEnablePeerAccess then maps the memory for
+// kernels of that device) -- memory imported through torch's tensor sharing is opened under the exporter's device and
+// faulted when a kernel of the importing rank's device stored into it (run r2g).
+int nnconv_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64) {
+  NNC_REQUIRE(dev_ptr && handle64 && bytes > 0, NNCONV_ERR_ARG, "ipc_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  void* p = nullptr;
+  NNC_CHECK_CUDA(cudaMalloc(&p, bytes));
+  NNC_CHECK_CUDA(cudaMemset(p, 0, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    NNC_CHECK_CUDA(e);
+  }
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return NNCONV_OK;
+}
+
+int nnconv_ipc_open(const unsigned char* handle64, void** dev_ptr) {
+  NNC_REQUIRE(dev_ptr && handle64, NNCONV_ERR_ARG, "ipc_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  NNC_CHECK_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return NNCONV_OK;
+}
+
+int nnconv_ipc_close(void* dev_ptr) {
+  if (dev_ptr) NNC_CHECK_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return NNCONV_OK;
+}
+
+int nnconv_ipc_free(void* dev_ptr) {
+  if (dev_ptr) NNC_CHECK_CUDA(cudaFree(dev_ptr));
+  return NNCONV_OK;
+}
+
 int nnconv_enable_peer_access(int peer_device) {
   int dev = 0;
   NNC_CHECK_CUDA(cudaGetDevice(&dev));

@@ -150,80 +150,101 @@ def halo_ranges(part):
     return out
 
 
+class _DevMem(object):
+    """Zero-copy torch view of raw device memory (``torch.as_tensor`` reads __cuda_array_interface__)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (int(ptr), False), 'version': 2}
+
+
 class PeerHalo(object):
-    """Double-buffered node-feature buffers of one rank, mapped into the two neighbours with CUDA IPC, plus one
-    flag word per direction.  ``advance(out, k)`` turns the result of application k into the input of application
-    k+1: ReLU + copy of the owned rows + peer stores of the boundary rows + flag (one small kernel pair), then a
-    one-thread wait kernel for the neighbours' flags.  Everything is stream-ordered on the device."""
+    """Double-buffered node-feature buffers of one rank plus one flag word per direction, in ONE peer-visible
+    allocation (``nnconv_ipc_alloc``) that the two neighbours map with CUDA IPC (``nnconv_ipc_open``, opened with the
+    importing rank's device current so that its kernels may store into it).  ``advance(out, k)`` turns the result of
+    application k into the input of application k+1: ReLU + copy of the owned rows + peer stores of the boundary rows
+    + flag (one small kernel pair), then a one-thread wait kernel for the neighbours' flags.  Everything is
+    stream-ordered on the device; no NCCL call between the applications."""
 
     def __init__(self, part, channels, device, group=None):
-        from torch.multiprocessing.reductions import reduce_tensor
         from . import _lib
         self.part, self.C, self.dev, self.group = part, channels, device, group
         self.L = _lib.lib()
         self._lib = _lib
-        self.bufs = [torch.zeros(part.n_local, channels, device=device) for _ in range(2)]
-        self.flags = torch.zeros(2, dtype=torch.int32, device=device)        # [from_up, from_down]
-        torch.cuda.synchronize(device)
-        payload = [reduce_tensor(t) for t in self.bufs + [self.flags]]
+        self.buf_bytes = ((part.n_local * channels * 4 + 255) // 256) * 256
+        nbytes = 2 * self.buf_bytes + 256
+        handle = ctypes.create_string_buffer(64)
+        ptr = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(self.L.nnconv_ipc_alloc(nbytes, ctypes.byref(ptr), handle))
+        self.base = ptr.value
+        raw = torch.as_tensor(_DevMem(self.base, nbytes), device=device)
+        self.bufs = [raw[i * self.buf_bytes:i * self.buf_bytes + part.n_local * channels * 4].view(torch.float32)
+                     .view(part.n_local, channels) for i in range(2)]
+        self.flags_ptr = self.base + 2 * self.buf_bytes                       # int32 [from_up, from_down]
         gathered = [None] * part.world
-        dist.all_gather_object(gathered, payload, group=group)
-        self._keep = []
+        dist.all_gather_object(gathered, (bytes(handle.raw), self.buf_bytes), group=group)
+        self._opened = []
 
         def open_(r):
-            ts = [fn(*args) for fn, args in gathered[r]]       # tensors on the NEIGHBOUR's device, mapped by CUDA IPC
-            self._keep.append(ts)
-            with torch.cuda.device(device):                    # this rank's kernels will store into them
-                _lib.check(self.L.nnconv_enable_peer_access(ts[0].device.index))
-            return ts
+            h, bb = gathered[r]
+            p = ctypes.c_void_p()
+            with torch.cuda.device(device):
+                _lib.check(self.L.nnconv_ipc_open(h, ctypes.byref(p)))
+            self._opened.append(p.value)
+            return dict(bufs=[p.value, p.value + bb], flags=p.value + 2 * bb)
         self.up = open_(part.rank - 1) if part.rank > 0 else None
         self.down = open_(part.rank + 1) if part.rank < part.world - 1 else None
         self.ranges = halo_ranges(part)
         self.seq = 0
         dist.barrier(group=group)
 
+    def close(self):
+        """Unmap the neighbours' buffers and free this rank's (collective: everybody unmaps before anybody frees)."""
+        if self.base is None:
+            return
+        torch.cuda.synchronize(self.dev)
+        for p in self._opened:
+            self.L.nnconv_ipc_close(ctypes.c_void_p(p))
+        self._opened = []
+        dist.barrier(group=self.group)
+        self.bufs = None
+        self.L.nnconv_ipc_free(ctypes.c_void_p(self.base))
+        self.base = None
+
     def load(self, x_local):
         """Input of application 0 (halo rows already correct: every rank slices the same global tensor)."""
         self.bufs[0].copy_(x_local)
         return self.bufs[0]
 
+    def _push(self, out_ptr, relu, own_lo, own_hi, nxt_ptr, k_next, up, dn):
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        vp = ctypes.c_void_p
+        u = up or (0, 0, 0)
+        d = dn or (0, 0, 0)
+        # my rows land in the neighbour ABOVE as its "from_down" halo / flag, in the neighbour BELOW as its "from_up"
+        self._lib.check(self.L.nnconv_halo_push(
+            vp(out_ptr), 1 if relu else 0, self.part.n_local, self.C, own_lo, own_hi, vp(nxt_ptr),
+            vp(self.up['bufs'][k_next]) if up else vp(0), u[0], u[1], u[2],
+            vp(self.down['bufs'][k_next]) if dn else vp(0), d[0], d[1], d[2],
+            vp(self.up['flags'] + 4) if up else vp(0), vp(self.down['flags']) if dn else vp(0), self.seq, vp(st)))
+        self._lib.check(self.L.nnconv_halo_wait(vp(self.flags_ptr) if up else vp(0), vp(self.flags_ptr + 4) if dn else vp(0),
+                                                self.seq, vp(st)))
+
     def advance(self, out, k, relu=True):
         nxt = self.bufs[(k + 1) % 2]
         self.seq += 1
-        up, dn = self.ranges['up'], self.ranges['down']
         p = self.part
-        st = torch.cuda.current_stream(self.dev).cuda_stream
-        vp = ctypes.c_void_p
-        peer_up = vp(self.up[(k + 1) % 2].data_ptr()) if up else vp(0)
-        peer_dn = vp(self.down[(k + 1) % 2].data_ptr()) if dn else vp(0)
-        # my rows land in the neighbour above as ITS "from_down" flag/halo, and vice versa
-        flag_up = vp(self.up[2].data_ptr() + 4) if up else vp(0)
-        flag_dn = vp(self.down[2].data_ptr()) if dn else vp(0)
-        u = up or (0, 0, 0)
-        d = dn or (0, 0, 0)
-        self._lib.check(self.L.nnconv_halo_push(vp(out.data_ptr()), 1 if relu else 0, p.n_local, self.C, p.own_lo, p.own_hi,
-                                                vp(nxt.data_ptr()), peer_up, u[0], u[1], u[2], peer_dn, d[0], d[1], d[2],
-                                                flag_up, flag_dn, self.seq, vp(st)))
-        self._lib.check(self.L.nnconv_halo_wait(vp(self.flags.data_ptr()) if up else vp(0),
-                                                vp(self.flags.data_ptr() + 4) if dn else vp(0), self.seq, vp(st)))
+        self._push(out.data_ptr(), relu, p.own_lo, p.own_hi, nxt.data_ptr(), (k + 1) % 2, self.ranges['up'], self.ranges['down'])
         return nxt
-
 
     def finish(self):
         """End-of-stack handshake (flags only): returns once both neighbours have retired their last application,
         so the next stack's pushes cannot overwrite halo rows a slower neighbour is still reading."""
         self.seq += 1
-        up, dn = self.ranges['up'], self.ranges['down']
-        st = torch.cuda.current_stream(self.dev).cuda_stream
-        vp = ctypes.c_void_p
-        b = self.bufs[0]
-        self._lib.check(self.L.nnconv_halo_push(vp(b.data_ptr()), 0, self.part.n_local, self.C, 0, 0, vp(b.data_ptr()),
-                                                vp(self.up[0].data_ptr()) if up else vp(0), 0, 0, 0,
-                                                vp(self.down[0].data_ptr()) if dn else vp(0), 0, 0, 0,
-                                                vp(self.up[2].data_ptr() + 4) if up else vp(0),
-                                                vp(self.down[2].data_ptr()) if dn else vp(0), self.seq, vp(st)))
-        self._lib.check(self.L.nnconv_halo_wait(vp(self.flags.data_ptr()) if up else vp(0),
-                                                vp(self.flags.data_ptr() + 4) if dn else vp(0), self.seq, vp(st)))
+        b = self.bufs[0].data_ptr()
+        up = (0, 0, 0) if self.up else None
+        dn = (0, 0, 0) if self.down else None
+        self._push(b, False, 0, 0, b, 0, up, dn)
 
 
 def partitioned_conv_stack_peer(conv_fn, x_local, part, edge_attr_local, depth, halo, relu_last=True):

@@ -184,6 +184,14 @@ int nnconv_halo_push(const float* out, int relu, int64_t n_local, int channels, 
                      int64_t dn_src0, int64_t dn_dst0, int64_t dn_rows, int* flag_up, int* flag_down, int seq,
                      void* stream);
 int nnconv_halo_wait(const int* flag_from_up, const int* flag_from_down, int seq, void* stream);
+/* Peer-visible device memory for the halo exchange: nnconv_ipc_alloc = cudaMalloc (zero-filled) + cudaIpcGetMemHandle
+ * (64-byte handle to send to the neighbour processes); nnconv_ipc_open maps a neighbour's allocation for kernels of
+ * the CURRENT device (cudaIpcOpenMemHandle with lazy peer access); _close / _free release them.  The only device
+ * allocation the library performs on the caller's behalf. */
+int nnconv_ipc_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64);
+int nnconv_ipc_open(const unsigned char* handle64, void** dev_ptr);
+int nnconv_ipc_close(void* dev_ptr);
+int nnconv_ipc_free(void* dev_ptr);
 /* kernels of the CURRENT device may load / store memory of `peer_device` afterwards (cudaDeviceEnablePeerAccess;
  * needed once per neighbour before nnconv_halo_push writes into its IPC-mapped buffers) */
 int nnconv_enable_peer_access(int peer_device);

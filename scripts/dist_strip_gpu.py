@@ -35,5 +35,6 @@ err_p = max(float((o - ref).abs().max() / ref.abs().max()) for o in outs_p)
 print('rank %d/%d rows [%d,%d) local edges %d  max rel err vs unpartitioned: all-gather %.3e, peer push %.3e' %
       (rank, world, part.row_lo, part.row_hi, part.edge_index.size(1), err, err_p), flush=True)
 assert err < 2e-3 and err_p < 2e-3
+halo.close()
 dist.barrier()
 dist.destroy_process_group()
