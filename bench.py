@@ -651,7 +651,11 @@ def main():
                      loss_first=losses[0], loss_last=losses[-1],
                      note='one 241^2-class graph per rank per step, L1 loss, Adam; gradients sum-reduced with one flat '
                           'all-reduce per step' if world > 1 else 'one graph per step, L1 loss, Adam')
-        del tmodel, opt
+        tmodel.conv1.invalidate()                 # the closure above still references the model: drop its 2 KB/edge
+        tmodel.conv1._tstate = None               # buffers (edge features + kept activations, ~94 GB at 241^2) explicitly
+        del step_train, tmodel, opt
+        import gc
+        gc.collect()
         torch.cuda.empty_cache()
     barrier()
 
