@@ -29,7 +29,7 @@ namespace {
 using namespace tc05;
 
 constexpr int kMaxSlots = 16;
-constexpr int kMaxAStages = 8;
+constexpr int kMaxAStages = 10;
 constexpr int kTU = 2;
 constexpr int kATileBytes = 128 * 64 * 2;
 constexpr int kYStages = 2;
@@ -526,9 +526,11 @@ bool apply_shape(int cout, int Kp, int ybn, ApplyShape* as) {
   const int bar_bytes = 1024;
   const int budget = 227 * 1024 - bar_bytes - kYStages * kYStageBytes;
   // fewest passes that leave >= 5 A stages (the h stream needs the bytes in flight), else >= 3
+  const int forced = options().apply_passes;
   for (int min_stages = 5; min_stages >= 3; min_stages -= 2) {
     for (int passes = 1; passes <= num_kc; ++passes) {
       if (num_kc % passes) continue;
+      if (forced > 0 && passes != forced && num_kc % forced == 0) continue;
       const int nb = num_kc / passes;
       if (nb > kMaxSlots) continue;
       if (passes > 1 && nb < 4) continue;   // too little time between a slot's release and its next use

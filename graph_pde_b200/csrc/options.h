@@ -10,6 +10,8 @@ struct Options {
   int ring;               // NNCONV_RING: Y ring depth of the fused kernel (2..8, default 3)
   int y_block_n;          // NNCONV_Y_BLOCKN: N tile of the Y pipeline (64 default | 128)
   int apply_stages;       // NNCONV_APPLY_STAGES: cap on the A stages of the fused kernel (0 = no cap)
+  int apply_passes;       // NNCONV_APPLY_PASSES: force the number of passes over the B-slot ring (0 = automatic): more
+                          // passes = fewer resident B slots = more A stages (bytes of the h stream in flight)
   int debug_scatter;      // NNCONV_DEBUG_SCATTER: timing experiments only (wrong results)
   int y_store_policy;     // NNCONV_Y_STORE_POLICY: 0 normal, 1 evict-last, 2 evict-first
   int l2_persist;         // NNCONV_L2_PERSIST: access-policy window over the Y ring; value = persisting-L2 set-aside in MB
