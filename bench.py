@@ -439,12 +439,15 @@ def strip_child_main(args):
 def run_strip_children(args, rank):
     """Every rank of the main bench spawns its own child (same RANK / WORLD_SIZE / LOCAL_RANK, MASTER_PORT + 23);
     rank 0 returns the child's JSON object (or an error record)."""
-    env = dict(os.environ)
+    # the children rendezvous among themselves: not through the elastic agent's store of the parent job (with
+    # TORCHELASTIC_USE_AGENT_STORE every rank is a CLIENT of MASTER_PORT and nobody would serve the new port: run r2h)
+    env = {k: v for k, v in os.environ.items() if not k.startswith('TORCHELASTIC_')}
     env['MASTER_PORT'] = str(int(env.get('MASTER_PORT', '29500')) + 23)
+    env.setdefault('MASTER_ADDR', '127.0.0.1')
     cmd = [sys.executable, os.path.abspath(__file__), '--strip-only', '--workload', args.workload, '--precision',
            args.precision, '--steps', str(args.steps)]
     try:
-        res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=420)
+        res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
         if rank != 0:
             return None
         lines = [l for l in res.stdout.splitlines() if l.startswith('{')]
