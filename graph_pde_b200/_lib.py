@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libnnconv_b200.so')
 CSRC = os.path.join(_HERE, 'csrc')
 
 OK = 0
+ABI_VERSION = 2        # include/nnconv_b200.h: NNCONV_B200_ABI_VERSION this binding was written against
 PREC = {'fp32': 0, 'f16': 1, 'fp16': 1, 'bf16': 2, 'f16x2': 3}
 AGGR = {'add': 0, 'mean': 1}
 FLOW = {'source_to_target': 0, 'target_to_source': 1}
@@ -124,6 +125,9 @@ def lib():
                                      c_vp]
     for name in SYMBOLS:
         getattr(L, name)
+    if L.nnconv_abi_version() != ABI_VERSION:
+        raise NNConvLibraryError('%s has ABI version %d, this binding needs %d: rebuild it (make -C %s)'
+                                 % (LIB_PATH, L.nnconv_abi_version(), ABI_VERSION, CSRC))
     _lib = L
     return L
 

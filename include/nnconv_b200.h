@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define NNCONV_B200_ABI_VERSION 1
+#define NNCONV_B200_ABI_VERSION 2   /* 2: round-2 entry points (backward_apply / backward_mlp, f16x2, options, halo, ...) */
 
 /* status codes */
 #define NNCONV_OK 0

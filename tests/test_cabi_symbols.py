@@ -34,7 +34,8 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version_and_size_queries(lib):
-    assert lib.nnconv_abi_version() == 1
+    from graph_pde_b200 import _lib
+    assert lib.nnconv_abi_version() == _lib.ABI_VERSION == 2
     ws, tmp = ctypes.c_size_t(), ctypes.c_size_t()
     assert lib.nnconv_plan_sizes(1000, 50, ctypes.byref(ws), ctypes.byref(tmp)) == 0
     assert ws.value > 1000 * 8 and tmp.value > 0

@@ -26,7 +26,7 @@ def _conv_cls():
 def test_library_loaded_and_device_ok(dev):
     from graph_pde_b200 import _lib
     L = _lib.lib()
-    assert L.nnconv_abi_version() == 1
+    assert L.nnconv_abi_version() == _lib.ABI_VERSION
     _lib.check(L.nnconv_init())
 
 
