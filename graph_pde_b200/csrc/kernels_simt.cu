@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(256) k_sgemm_nt(SgemmArgs a) {
   }
 }
 
-// ---- formulation B application: one warp per source, out[dst_e, :] += (x_src . K_e) / deg for its edges.
+// ---- formulation B application: one warp per edge, out[dst_e, :] += (x_src . K_e) / deg.
 // K_e is [cin, cout] 16-bit row-major (8 KB at 64 x 64): for a fixed input channel i the 32 lanes read one
 // contiguous row of cout 16-bit values (lane -> 2 columns), so the pass streams Kmat at full sector efficiency.
 template <typename T2>
@@ -419,36 +419,41 @@ template <>
 __device__ __forceinline__ float2 cvt2<__nv_bfloat162>(__nv_bfloat162 v) { return __bfloat1622float2(v); }
 
 template <typename T2>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 k_apply_edge(const T2* __restrict__ Kmat, const float* __restrict__ x, const int* __restrict__ src_nodes,
              const int* __restrict__ group_ptr, const int* __restrict__ dst_sorted, const float* __restrict__ inv_deg,
-             int S, int cin, int cout, float* __restrict__ out) {
+             int S, int64_t E, int cin, int cout, float* __restrict__ out) {
+  // one warp per EDGE (sorted position p): parallelism = E warps whatever the degree distribution is (one warp per
+  // source serialised the 18-55 edges of MGKN's coarse levels and ran 3x slower than formulation C, run r2i)
   extern __shared__ float sxe[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  const int c = blockIdx.x * 4 + warp;
-  if (c >= S) return;
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * (blockDim.x / 32) + warp;
+  if (p >= E) return;
+  // compact source of this edge: the last c with group_ptr[c] <= p (all lanes search together: broadcast loads)
+  int lo = 0, hi = S;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(group_ptr + mid) <= p) lo = mid; else hi = mid;
+  }
   float* sx = sxe + warp * cin;
-  const int n = src_nodes[c];
-  for (int i = lane; i < cin; i += 32) sx[i] = x[static_cast<int64_t>(n) * cin + i];
+  const int n = __ldg(src_nodes + lo);
+  for (int i = lane; i < cin; i += 32) sx[i] = __ldg(x + static_cast<int64_t>(n) * cin + i);
   __syncwarp();
-  const int e0 = group_ptr[c], e1 = group_ptr[c + 1];
   const int half_cout = cout / 2;
-  for (int p = e0; p < e1; ++p) {
-    const T2* Kp = Kmat + static_cast<int64_t>(p) * cin * half_cout;
-    const int d = dst_sorted[p];
-    const float sc = inv_deg ? inv_deg[d] : 1.f;
-    for (int o2 = lane; o2 < half_cout; o2 += 32) {
-      float ax = 0.f, ay = 0.f;
-#pragma unroll 8
-      for (int i = 0; i < cin; ++i) {
-        const float2 k = cvt2<T2>(Kp[i * half_cout + o2]);
-        ax = fmaf(sx[i], k.x, ax);
-        ay = fmaf(sx[i], k.y, ay);
-      }
-      float* o = out + static_cast<int64_t>(d) * cout + 2 * o2;
-      atomicAdd(o, ax * sc);
-      atomicAdd(o + 1, ay * sc);
+  const T2* Kp = Kmat + p * cin * half_cout;
+  const int d = __ldg(dst_sorted + p);
+  const float sc = inv_deg ? __ldg(inv_deg + d) : 1.f;
+  for (int o2 = lane; o2 < half_cout; o2 += 32) {
+    float ax = 0.f, ay = 0.f;
+#pragma unroll 16
+    for (int i = 0; i < cin; ++i) {
+      const float2 k = cvt2<T2>(Kp[i * half_cout + o2]);
+      ax = fmaf(sx[i], k.x, ax);
+      ay = fmaf(sx[i], k.y, ay);
     }
+    float* o = out + static_cast<int64_t>(d) * cout + 2 * o2;
+    atomicAdd(o, ax * sc);
+    atomicAdd(o + 1, ay * sc);
   }
 }
 
@@ -605,16 +610,16 @@ int launch_src_prep(int prec, const float* x, const int* src_nodes, int S, int c
 int launch_apply_edge(int prec, const Plan* P, const Weights* W, const void* Kmat, const float* x, int aggr_mean, float* out,
                       cudaStream_t st) {
   const int S = P->n_src;
-  if (S <= 0) return NNCONV_OK;
-  const unsigned g = (unsigned)ceil_div(S, 4);
-  const size_t sm = sizeof(float) * 4 * W->cin;
+  if (S <= 0 || P->E <= 0) return NNCONV_OK;
+  const unsigned g = (unsigned)ceil_div64(P->E, 8);
+  const size_t sm = sizeof(float) * 8 * W->cin;
   const float* inv_deg = aggr_mean ? P->inv_deg : nullptr;
   if (prec == PREC_BF16)
-    k_apply_edge<__nv_bfloat162><<<g, 128, sm, st>>>(static_cast<const __nv_bfloat162*>(Kmat), x, P->src_nodes, P->group_ptr,
-                                                     P->dst_sorted, inv_deg, S, W->cin, W->cout, out);
+    k_apply_edge<__nv_bfloat162><<<g, 256, sm, st>>>(static_cast<const __nv_bfloat162*>(Kmat), x, P->src_nodes, P->group_ptr,
+                                                     P->dst_sorted, inv_deg, S, P->E, W->cin, W->cout, out);
   else
-    k_apply_edge<__half2><<<g, 128, sm, st>>>(static_cast<const __half2*>(Kmat), x, P->src_nodes, P->group_ptr, P->dst_sorted,
-                                              inv_deg, S, W->cin, W->cout, out);
+    k_apply_edge<__half2><<<g, 256, sm, st>>>(static_cast<const __half2*>(Kmat), x, P->src_nodes, P->group_ptr, P->dst_sorted,
+                                              inv_deg, S, P->E, W->cin, W->cout, out);
   NNC_CHECK_LAUNCH();
   return NNCONV_OK;
 }

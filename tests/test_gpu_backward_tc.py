@@ -257,9 +257,10 @@ def test_kept_and_recomputed_hidden_activations_give_the_same_gradients(monkeypa
     lin = [m for m in mlp.layers if isinstance(m, torch.nn.Linear)]
     ws, bs = [l.weight.detach().clone() for l in lin], [l.bias.detach().clone() for l in lin]
     grads = []
+    root = torch.randn(w, w, generator=gen) * 0.1
     for budget in (64 << 30, 0):
         monkeypatch.setattr(nn_conv, '_KEEP_ACTS_MAX_BYTES', budget)
-        conv = make_conv(NNConv_old, ws, bs, torch.randn(w, w) * 0.1, None, 'mean', w, w, 'f16', DEV)
+        conv = make_conv(NNConv_old, ws, bs, root, None, 'mean', w, w, 'f16', DEV)
         xd = x.to(DEV).requires_grad_(True)
         h = torch.relu(conv(xd, ei.to(DEV), ea.to(DEV)))
         kept = conv._tstate.acts is not None
