@@ -457,6 +457,42 @@ k_apply_edge(const T2* __restrict__ Kmat, const float* __restrict__ x, const int
   }
 }
 
+// variant for very low out-degree (E <= 8 S, the 1-D multipole stencils): one warp per SOURCE loads x_src once and walks
+// its 2-4 edges -- no per-edge source search, measured 1.27 vs 1.62 ms per config-5 forward (runs r2e / r2j)
+template <typename T2>
+__global__ void __launch_bounds__(128)
+k_apply_edge_src(const T2* __restrict__ Kmat, const float* __restrict__ x, const int* __restrict__ src_nodes,
+                 const int* __restrict__ group_ptr, const int* __restrict__ dst_sorted, const float* __restrict__ inv_deg,
+                 int S, int cin, int cout, float* __restrict__ out) {
+  extern __shared__ float sxe[];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int c = blockIdx.x * 4 + warp;
+  if (c >= S) return;
+  float* sx = sxe + warp * cin;
+  const int n = src_nodes[c];
+  for (int i = lane; i < cin; i += 32) sx[i] = x[static_cast<int64_t>(n) * cin + i];
+  __syncwarp();
+  const int e0 = group_ptr[c], e1 = group_ptr[c + 1];
+  const int half_cout = cout / 2;
+  for (int p = e0; p < e1; ++p) {
+    const T2* Kp = Kmat + static_cast<int64_t>(p) * cin * half_cout;
+    const int d = dst_sorted[p];
+    const float sc = inv_deg ? inv_deg[d] : 1.f;
+    for (int o2 = lane; o2 < half_cout; o2 += 32) {
+      float ax = 0.f, ay = 0.f;
+#pragma unroll 8
+      for (int i = 0; i < cin; ++i) {
+        const float2 k = cvt2<T2>(Kp[i * half_cout + o2]);
+        ax = fmaf(sx[i], k.x, ax);
+        ay = fmaf(sx[i], k.y, ay);
+      }
+      float* o = out + static_cast<int64_t>(d) * cout + 2 * o2;
+      atomicAdd(o, ax * sc);
+      atomicAdd(o + 1, ay * sc);
+    }
+  }
+}
+
 template <typename T>
 int launch_pad_convert_t(const float* src, int R, int C, void* dst, int Rp, int Cp, cudaStream_t st) {
   int64_t total = static_cast<int64_t>(Rp) * Cp;
@@ -611,9 +647,21 @@ int launch_apply_edge(int prec, const Plan* P, const Weights* W, const void* Kma
                       cudaStream_t st) {
   const int S = P->n_src;
   if (S <= 0 || P->E <= 0) return NNCONV_OK;
+  const float* inv_deg = aggr_mean ? P->inv_deg : nullptr;
+  if (P->E <= 8 * static_cast<int64_t>(S)) {       // a handful of edges per source: warp per source
+    const unsigned g = (unsigned)ceil_div(S, 4);
+    const size_t sm = sizeof(float) * 4 * W->cin;
+    if (prec == PREC_BF16)
+      k_apply_edge_src<__nv_bfloat162><<<g, 128, sm, st>>>(static_cast<const __nv_bfloat162*>(Kmat), x, P->src_nodes,
+                                                           P->group_ptr, P->dst_sorted, inv_deg, S, W->cin, W->cout, out);
+    else
+      k_apply_edge_src<__half2><<<g, 128, sm, st>>>(static_cast<const __half2*>(Kmat), x, P->src_nodes, P->group_ptr,
+                                                    P->dst_sorted, inv_deg, S, W->cin, W->cout, out);
+    NNC_CHECK_LAUNCH();
+    return NNCONV_OK;
+  }
   const unsigned g = (unsigned)ceil_div64(P->E, 8);
   const size_t sm = sizeof(float) * 8 * W->cin;
-  const float* inv_deg = aggr_mean ? P->inv_deg : nullptr;
   if (prec == PREC_BF16)
     k_apply_edge<__nv_bfloat162><<<g, 256, sm, st>>>(static_cast<const __nv_bfloat162*>(Kmat), x, P->src_nodes, P->group_ptr,
                                                      P->dst_sorted, inv_deg, S, P->E, W->cin, W->cout, out);
