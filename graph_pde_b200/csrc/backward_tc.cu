@@ -512,6 +512,11 @@ struct DhArgs {
   int T, Kp, BN, n_nb;      // n_nb = Kp / BN
   const uint16_t* h;        // chunk-major edge features (the ReLU mask)
   uint16_t* dz;             // [batch edges, Kp] row-major
+  // optional fused bias gradient: colsum[k * colsum_stride] += sum over the batch's edges of dz[e, k] (fp32, unscaled by
+  // the caller's power-of-two factor like dz itself).  Column sums are formed per warp piece through a [32][33] shared
+  // transpose and accumulated in a per-warp shared array; needs 4 * (4224 + 4 * Kp) extra bytes of shared memory.
+  float* colsum;
+  int colsum_stride;
 };
 
 template <int FMT>
@@ -530,6 +535,8 @@ k_dh(const __grid_constant__ Maps8 tmA, const __grid_constant__ CUtensorMap tmB,
   uint64_t* tfull = b_empty + kDhBStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_tr = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);     // [4][32][33]  (colsum only)
+  float* s_cs = s_tr + 4 * 32 * 33;                                                     // [4][Kp]
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x / 32), 0), lane = threadIdx.x % 32;
 
   if (warp == 0 && lane == 0) {
@@ -606,6 +613,11 @@ k_dh(const __grid_constant__ Maps8 tmA, const __grid_constant__ CUtensorMap tmB,
     }
   } else {
     const int quarter = warp % 4;
+    float* my_tr = s_tr + quarter * 32 * 33;
+    float* my_cs = s_cs + quarter * a.Kp;
+    if (a.colsum != nullptr)
+      for (int k = lane; k < a.Kp; k += 32) my_cs[k] = 0.f;
+    __syncwarp();
     int it = 0;
     for (int t = a.tile0 + blockIdx.x; t < a.tile1; t += gridDim.x) {
       const int e0 = __ldg(a.tile_e0 + t), cnt = __ldg(a.tile_cnt + t);
@@ -620,8 +632,8 @@ k_dh(const __grid_constant__ Maps8 tmA, const __grid_constant__ CUtensorMap tmB,
           uint32_t v[32];
           tmem_ld32(tb + cc, v);
           tmem_ld_wait();
+          const int k0 = nb * a.BN + cc;
           if (ok) {
-            const int k0 = nb * a.BN + cc;
             const uint16_t* hp = a.h + (static_cast<int64_t>(k0 >> 6) * a.e_pad + e0 + r) * 64 + (k0 & 63);
             uint32_t pk[16];
 #pragma unroll
@@ -633,16 +645,35 @@ k_dh(const __grid_constant__ Maps8 tmA, const __grid_constant__ CUtensorMap tmB,
                 const float f0 = (mw[j] & 0x7FFFu) ? __uint_as_float(v[8 * q + 2 * j]) : 0.f;
                 const float f1 = (mw[j] & 0x7FFF0000u) ? __uint_as_float(v[8 * q + 2 * j + 1]) : 0.f;
                 pk[4 * q + j] = pack2<FMT>(f0, f1);
+                v[8 * q + 2 * j] = __float_as_uint(f0);
+                v[8 * q + 2 * j + 1] = __float_as_uint(f1);
               }
             }
             uint16_t* dst = a.dz + static_cast<int64_t>(e0 - a.e_base + r) * a.Kp + k0;
             st_global_v8(dst, pk);
             st_global_v8(dst + 16, pk + 8);
           }
+          if (a.colsum != nullptr) {          // column sums of this warp's [32 rows x 32 columns] piece
+#pragma unroll
+            for (int j = 0; j < 32; ++j) my_tr[lane * 33 + j] = ok ? __uint_as_float(v[j]) : 0.f;
+            __syncwarp();
+            float cs = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) cs += my_tr[rr * 33 + lane];
+            my_cs[k0 + lane] += cs;
+            __syncwarp();
+          }
         }
         fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[as]);
+      }
+    }
+    if (a.colsum != nullptr) {
+      __syncwarp();
+      for (int k = lane; k < a.Kp; k += 32) {
+        const float v = my_cs[k];
+        if (v != 0.f) atomicAdd(a.colsum + static_cast<int64_t>(k) * a.colsum_stride, v);
       }
     }
   }
@@ -925,8 +956,13 @@ int backward_mlp_tc(const Plan* P, const Weights* W, const float* edge_attr, con
     NNC_CHECK_CUDA(cudaFuncSetAttribute(k_dh<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int dh_smem = T * kDhAChunk + kDhBStages * BN * 128 + 1024;
+  int dh_smem = T * kDhAChunk + kDhBStages * BN * 128 + 1024;
   NNC_REQUIRE(dh_smem <= 227 * 1024, NNCONV_ERR_UNSUPPORTED, "backward_mlp: T=%d applications do not fit shared memory", T);
+  // bias gradient of the top hidden layer fused into k_dh (one pass over dz_{L-1} saved) when the transpose + column
+  // accumulators fit next to the operand stages; layer 1 (nl == 2) needs the full dz^T A1 product anyway
+  const int cs_bytes = 4 * (32 * 33 * 4 + 4 * Kp);
+  const bool fuse_colsum = nl >= 3 && dh_smem + cs_bytes <= 227 * 1024;
+  if (fuse_colsum) dh_smem += cs_bytes;
   int c0 = 0;
   while (c0 < S) {
     int c1 = c0;
@@ -986,6 +1022,8 @@ int backward_mlp_tc(const Plan* P, const Weights* W, const float* edge_attr, con
       a.tile0 = htp[c0]; a.tile1 = htp[c1]; a.c0 = c0; a.Sb = nb; a.e_base = e_base; a.e_pad = static_cast<int>(e_pad);
       a.T = T; a.Kp = Kp; a.BN = BN; a.n_nb = Kp / BN;
       a.h = static_cast<const uint16_t*>(h); a.dz = dzA;
+      a.colsum = fuse_colsum ? reinterpret_cast<float*>(base + L.off_D[nl - 1]) + 3 * k_in : nullptr;
+      a.colsum_stride = 64;
       const int tiles = a.tile1 - a.tile0;
       const int grid = tiles < tc_num_sms() ? tiles : tc_num_sms();
       if (bf) k_dh<1><<<grid, 192, dh_smem, st>>>(tmA, tmB, a);
@@ -1008,9 +1046,12 @@ int backward_mlp_tc(const Plan* P, const Weights* W, const float* edge_attr, con
     uint16_t* nxt = dzB;
     for (int l = nl - 1; l >= 1; --l) {
       float* Dl = reinterpret_cast<float*>(base + L.off_D[l]);
-      // D_l[j, :] += dz_l^T A1   (column 3*k_in = the bias gradient; for l = 1 also dW_1 in split form)
-      s = launch_gemm_tn(W->prec, cur, W->kp[l], 0, A1, 64, 0, n, W->kp[l], 64, Dl, 64, 1.f, nullptr, st);
-      if (s) return s;
+      // D_l[j, :] += dz_l^T A1   (column 3*k_in = the bias gradient; for l = 1 also dW_1 in split form); the top
+      // layer's column comes out of k_dh when fused
+      if (!(fuse_colsum && l == nl - 1)) {
+        s = launch_gemm_tn(W->prec, cur, W->kp[l], 0, A1, 64, 0, n, W->kp[l], 64, Dl, 64, 1.f, nullptr, st);
+        if (s) return s;
+      }
       if (l >= 2) {
         float* dWl = reinterpret_cast<float*>(base + L.off_dW[l]);
         s = launch_gemm_tn(W->prec, cur, W->kp[l], 0, act[l - 1], W->kp[l - 1], 0, n, W->kp[l], W->kp[l - 1], dWl,
