@@ -228,6 +228,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const uint32_t* vv = v[cc & 1];
           uint32_t packed[16], packed_lo[EPI == EPI_SPLIT ? 16 : 1];
           float vm[4] = {0.f, 0.f, 0.f, 0.f};       // four independent max chains (one chain of 32 is latency bound)
+          uint32_t mkw[16];                         // EPI_MASK: the row's 32 stored activations (64 B, four 16-byte loads)
+          if (EPI == EPI_MASK && row_ok) {
+            const uint4* mp = reinterpret_cast<const uint4*>(a.mask + static_cast<int64_t>(row) * a.mask_ld + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 m = __ldg(mp + q);
+              mkw[4 * q] = m.x; mkw[4 * q + 1] = m.y; mkw[4 * q + 2] = m.z; mkw[4 * q + 3] = m.w;
+            }
+          }
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             float f[4] = {__uint_as_float(vv[4 * j4]), __uint_as_float(vv[4 * j4 + 1]),
@@ -251,11 +260,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             if (EPI == EPI_MASK) {
               if (row_ok) {
-                const uint2 mk = __ldg(reinterpret_cast<const uint2*>(a.mask + static_cast<int64_t>(row) * a.mask_ld + col0) + j4);
-                if ((mk.x & 0x7FFFu) == 0u) f[0] = 0.f;
-                if ((mk.x & 0x7FFF0000u) == 0u) f[1] = 0.f;
-                if ((mk.y & 0x7FFFu) == 0u) f[2] = 0.f;
-                if ((mk.y & 0x7FFF0000u) == 0u) f[3] = 0.f;
+                const uint32_t mx = mkw[2 * j4], my = mkw[2 * j4 + 1];
+                if ((mx & 0x7FFFu) == 0u) f[0] = 0.f;
+                if ((mx & 0x7FFF0000u) == 0u) f[1] = 0.f;
+                if ((my & 0x7FFFu) == 0u) f[2] = 0.f;
+                if ((my & 0x7FFF0000u) == 0u) f[3] = 0.f;
               }
             }
             if (EPI == EPI_F32) {
@@ -433,8 +442,8 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
   a.mask = static_cast<const uint16_t*>(mask);
   a.mask_ld = mask_ld;
   a.out_f32 = out_f32;
-  NNC_REQUIRE(mask == nullptr || (mask_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(mask) & 7) == 0), NNCONV_ERR_ARG,
-              "gemm_tc: mask must be 8-byte aligned with mask_ld a multiple of 4");
+  NNC_REQUIRE(mask == nullptr || (mask_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(mask) & 15) == 0), NNCONV_ERR_ARG,
+              "gemm_tc: mask must be 16-byte aligned with mask_ld a multiple of 8");
   {
     TraceHandle th = trace_get();
     static unsigned int launch_seq = 0;
