@@ -67,6 +67,7 @@ struct ApplyArgs {
   int* okC;
   int* cntU;              // units handed out so far (one counter per application)
   unsigned long long y_store_policy;   // L2 eviction-priority hint of the Y ring stores
+  unsigned long long a_policy;         // ... of the h stream loads
   int debug_scatter;      // timing experiments only (NNCONV_DEBUG_SCATTER): 1 = drop the scatter, 2 = plain stores
   TraceBuf trace;
 };
@@ -238,7 +239,7 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
             mbar_wait(&a_empty[stage], phase ^ 1u);
             if (elect_one()) {
               mbar_arrive_expect_tx(&a_full[stage], a_bytes);
-              tma_load_2d(smem_a + stage * kATileBytes, mh, &a_full[stage], 0, ja * a.e_pad + te0[ti], kEvictFirst);
+              tma_load_2d(smem_a + stage * kATileBytes, mh, &a_full[stage], 0, ja * a.e_pad + te0[ti], a.a_policy);
             }
             __syncwarp();
             if (++stage == a.a_stages) { stage = 0; phase ^= 1u; }
@@ -649,6 +650,7 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
   a.y_scale = (split && W->wscale) ? W->wscale + 2 * W->n_layers + 1 : nullptr;
   a.NY = NY; a.num_kx = xmul * W->cin_p / 64; a.Yring = Yring;
   a.y_store_policy = opt.y_store_policy == 1 ? kEvictLast : opt.y_store_policy == 2 ? kEvictFirst : kEvictNormal;
+  a.a_policy = opt.apply_a_policy == 1 ? kEvictNormal : kEvictFirst;
   a.debug_scatter = opt.debug_scatter;   // wrong results, timing only
   a.cntY = flags; a.cntC = flags + flags_stride; a.okY = flags + 2 * flags_stride; a.okC = flags + 3 * flags_stride;
   a.cntU = flags + 4 * flags_stride;

@@ -12,6 +12,8 @@ struct Options {
   int apply_stages;       // NNCONV_APPLY_STAGES: cap on the A stages of the fused kernel (0 = no cap)
   int apply_passes;       // NNCONV_APPLY_PASSES: force the number of passes over the B-slot ring (0 = automatic): more
                           // passes = fewer resident B slots = more A stages (bytes of the h stream in flight)
+  int apply_a_policy;     // NNCONV_APPLY_A_POLICY: L2 hint of the h stream in the fused kernel: 0 evict-first (default), 1 normal
+  int tmap_promo;         // NNCONV_TMAP_PROMO: L2 promotion of operand tensor maps: 2 = 256 B (default), 1 = 128 B, 0 = none
   int debug_scatter;      // NNCONV_DEBUG_SCATTER: timing experiments only (wrong results)
   int y_store_policy;     // NNCONV_Y_STORE_POLICY: 0 normal, 1 evict-last, 2 evict-first
   int l2_persist;         // NNCONV_L2_PERSIST: access-policy window over the Y ring; value = persisting-L2 set-aside in MB

@@ -76,7 +76,9 @@ static int make_tmap_kind(CUtensorMap* out, int is_bf16, const void* base, uint6
   CUresult r = g_encode(out, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                         const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         kind == 1 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        options().tmap_promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                        : options().tmap_promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                    : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   NNC_REQUIRE(r == CUDA_SUCCESS, NNCONV_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   TmapEntry& e = t_cache[t_cache_next];
