@@ -35,6 +35,8 @@ constexpr int kATileBytes = 128 * 64 * 2;
 constexpr int kYStages = 2;
 constexpr int kThreads = 384;
 constexpr int kQueue = 8;                  // unit queue between the scheduler and the MMA / epilogue warps
+constexpr int kScatterPitch = 272;         // bytes per staged edge row (64 fp32 + 16 B: bank-conflict-free v4 stores)
+constexpr int kScatterBytes = 4 * 32 * kScatterPitch;
 
 struct ApplyArgs {
   // plan
@@ -68,6 +70,7 @@ struct ApplyArgs {
   int* cntU;              // units handed out so far (one counter per application)
   unsigned long long y_store_policy;   // L2 eviction-priority hint of the Y ring stores
   unsigned long long a_policy;         // ... of the h stream loads
+  int scatter_mode;                    // 1: rows staged in shared memory + cp.reduce.async.bulk (see options.h)
   int debug_scatter;      // timing experiments only (NNCONV_DEBUG_SCATTER): 1 = drop the scatter, 2 = plain stores
   TraceBuf trace;
 };
@@ -111,6 +114,8 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
   uint64_t* q_empty = q_full + kQueue;   // [kQueue] 5 arrivals (MMA issuer + 4 epilogue warps)
   int4* q_ent = reinterpret_cast<int4*>(q_empty + kQueue);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_ent + kQueue);
+  // scatter staging (scatter_mode 1): 4 epilogue warps x 32 rows x kScatterPitch bytes, after the 1 KB barrier block
+  uint8_t* smem_sc = reinterpret_cast<uint8_t*>(bars) + 1024;
 
   // shfl: the warp index is warp-uniform for the compiler (see tc05::elect_one)
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x / 32), 0), lane = threadIdx.x % 32;
@@ -328,6 +333,7 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
       }
       const float* cv = a.cvec + static_cast<int64_t>(en.z) * a.cout;
       const float xsc = __ldg(a.xs + en.z);
+      const uint32_t my_row = smem_u32(smem_sc) + static_cast<uint32_t>(((warp - 2) * 32 + lane) * kScatterPitch);
       mbar_wait(&tfull[as], (it >> 1) & 1);
       fence_after_sync();
       if (warp == 2 && lane == 0) {
@@ -341,12 +347,24 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
       for (int ti = 0; ti < kTU; ++ti) {
         if (ti < en.y) {
           float* orow = a.out + static_cast<int64_t>(d[ti]) * a.cout;
+          if (a.scatter_mode == 1) bulk_wait_read0();     // this lane's previous row has left its staging slot
 #pragma unroll 1
           for (int cc = 0; cc < a.cout; cc += 16) {
             uint32_t v[16];
             tmem_ld16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (as * kTU + ti) * a.cout + cc, v);
             tmem_ld_wait();
-            if (ok[ti] && a.debug_scatter == 2) {
+            if (a.scatter_mode == 1) {
+              // the lane's own row: 4 x 16 B into its staging slot (pitch 272 B: conflict-free 8-lane phases)
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 cq = __ldg(reinterpret_cast<const float4*>(cv + cc) + q);
+                st_shared_v4(my_row + static_cast<uint32_t>((cc + 4 * q) * 4),
+                             __float_as_uint(fmaf(__uint_as_float(v[4 * q + 0]), xsc, cq.x) * sc[ti]),
+                             __float_as_uint(fmaf(__uint_as_float(v[4 * q + 1]), xsc, cq.y) * sc[ti]),
+                             __float_as_uint(fmaf(__uint_as_float(v[4 * q + 2]), xsc, cq.z) * sc[ti]),
+                             __float_as_uint(fmaf(__uint_as_float(v[4 * q + 3]), xsc, cq.w) * sc[ti]));
+              }
+            } else if (ok[ti] && a.debug_scatter == 2) {
 #pragma unroll
               for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<float4*>(orow + cc + 4 * q) =
@@ -363,6 +381,11 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
               }
             }
           }
+          if (a.scatter_mode == 1) {
+            fence_proxy_async_smem();                       // generic-proxy writes of this lane -> async proxy
+            if (ok[ti]) bulk_reduce_add_f32(orow, my_row, static_cast<uint32_t>(a.cout) * 4u);
+            bulk_commit();
+          }
         }
       }
       fence_before_sync();
@@ -370,6 +393,7 @@ k_apply_tc(const __grid_constant__ HMaps tmH, const __grid_constant__ CUtensorMa
       if (lane == 0) mbar_arrive(&tempty[as]);
       ++it;
     }
+    if (a.scatter_mode == 1) bulk_wait0();                  // every row has been added before the CTA retires
   } else if (warp == 6) {
     // ============================================================== Y GEMM: TMA producer (whole warp, elected lane)
     const int n_blocks = a.NY / kYBlockN;
@@ -524,7 +548,7 @@ bool apply_shape(int cout, int Kp, int ybn, ApplyShape* as) {
   if (cout % 16 != 0 || cout < 16 || 2 * kTU * cout > 256 || Kp % 64 != 0) return false;
   const int num_kc = Kp / 64;
   const int b_stride = (cout * 128 + 1023) & ~1023;
-  const int bar_bytes = 1024;
+  const int bar_bytes = 1024 + (options().scatter_mode == 1 ? kScatterBytes : 0);
   const int budget = 227 * 1024 - bar_bytes - kYStages * kYStageBytes;
   // fewest passes that leave >= 5 A stages (the h stream needs the bytes in flight), else >= 3
   const int forced = options().apply_passes;
@@ -651,6 +675,7 @@ int launch_apply_tc(int prec, const Plan* P, const Weights* W, const void* h, co
   a.NY = NY; a.num_kx = xmul * W->cin_p / 64; a.Yring = Yring;
   a.y_store_policy = opt.y_store_policy == 1 ? kEvictLast : opt.y_store_policy == 2 ? kEvictFirst : kEvictNormal;
   a.a_policy = opt.apply_a_policy == 1 ? kEvictNormal : kEvictFirst;
+  a.scatter_mode = (opt.scatter_mode == 1 && W->cout <= 64) ? 1 : 0;
   a.debug_scatter = opt.debug_scatter;   // wrong results, timing only
   a.cntY = flags; a.cntC = flags + flags_stride; a.okY = flags + 2 * flags_stride; a.okC = flags + 3 * flags_stride;
   a.cntU = flags + 4 * flags_stride;

@@ -185,6 +185,14 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
+// Bulk reduction smem -> global through the async proxy (TMA engine): global[0..bytes) += smem[0..bytes) as fp32 adds.
+// bytes multiple of 16, both addresses 16-byte aligned; completion through the issuing thread's bulk groups.
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, uint32_t smem_src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+               ::"l"(gdst), "r"(smem_src), "r"(bytes)
+               : "memory");
+}
+
 // 256-bit global store (sm_100+): one full 32-byte sector per thread per instruction.
 __device__ __forceinline__ void st_global_v8(void* addr, const uint32_t* v) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
