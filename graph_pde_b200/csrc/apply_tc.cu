@@ -550,9 +550,9 @@ bool apply_shape(int cout, int Kp, int ybn, ApplyShape* as) {
   const int b_stride = (cout * 128 + 1023) & ~1023;
   const int bar_bytes = 1024 + (options().scatter_mode == 1 ? kScatterBytes : 0);
   const int budget = 227 * 1024 - bar_bytes - kYStages * kYStageBytes;
-  // fewest passes that leave >= 5 A stages (the h stream needs the bytes in flight), else >= 3
+  // fewest passes that leave >= 7 A stages (the h stream needs the bytes in flight), else >= 5, else >= 3
   const int forced = options().apply_passes;
-  for (int min_stages = 5; min_stages >= 3; min_stages -= 2) {
+  for (int min_stages = 7; min_stages >= 3; min_stages -= 2) {
     for (int passes = 1; passes <= num_kc; ++passes) {
       if (num_kc % passes) continue;
       if (forced > 0 && passes != forced && num_kc % forced == 0) continue;

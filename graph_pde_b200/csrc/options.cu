@@ -23,7 +23,7 @@ const Entry kEntries[] = {
     {"apply_passes", "NNCONV_APPLY_PASSES", &Options::apply_passes, 0},
     {"apply_a_policy", "NNCONV_APPLY_A_POLICY", &Options::apply_a_policy, 0},
     {"tmap_promo", "NNCONV_TMAP_PROMO", &Options::tmap_promo, 2},
-    {"scatter_mode", "NNCONV_SCATTER_MODE", &Options::scatter_mode, 0},
+    {"scatter_mode", "NNCONV_SCATTER_MODE", &Options::scatter_mode, 1},
     {"debug_scatter", "NNCONV_DEBUG_SCATTER", &Options::debug_scatter, 0},
     {"y_store_policy", "NNCONV_Y_STORE_POLICY", &Options::y_store_policy, 0},
     {"l2_persist", "NNCONV_L2_PERSIST", &Options::l2_persist, 0},
