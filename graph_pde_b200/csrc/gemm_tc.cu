@@ -83,7 +83,8 @@ struct GemmCfg {
 // tiny basic blocks and the K = 64 first-layer GEMM, which is epilogue bound, ran 2.4x slower: run r2b):
 //   EPI_PLAIN bias / ReLU / 16-bit store     EPI_SPLIT the same, written as (hi, lo) fp16 pairs (PREC_F16X2)
 //   EPI_MASK  ReLU-derivative mask from a stored activation (backward)     EPI_F32 fp32 output, plain stores
-enum { EPI_PLAIN = 0, EPI_SPLIT = 1, EPI_MASK = 2, EPI_F32 = 3 };
+//   EPI_NOCHECK = EPI_PLAIN without the fp16 range tracking (bf16 outputs, option overflow_check = 0, test hooks)
+enum { EPI_PLAIN = 0, EPI_SPLIT = 1, EPI_MASK = 2, EPI_F32 = 3, EPI_NOCHECK = 4 };
 
 template <int BLOCK_N, int FMT, int SMALL, int EPI>
 __global__ void __launch_bounds__(320, SMALL ? 2 : 1)
@@ -489,6 +490,11 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
     return launch_gemm_cfg<64, 0, 0, EPI_SPLIT>(tmA, tmB, tmC, a, st, pdl);
   }
 #undef NNC_GEMM_EPI
+  if (!bf && !small && a.overflow == nullptr) {      // fp16 output nobody wants range-checked
+    if (BN == 256) return launch_gemm_cfg<256, 0, 0, EPI_NOCHECK>(tmA, tmB, tmC, a, st, pdl);
+    if (BN == 128) return launch_gemm_cfg<128, 0, 0, EPI_NOCHECK>(tmA, tmB, tmC, a, st, pdl);
+    return launch_gemm_cfg<64, 0, 0, EPI_NOCHECK>(tmA, tmB, tmC, a, st, pdl);
+  }
   if (small) return bf ? launch_gemm_cfg<128, 1, 1>(tmA, tmB, tmC, a, st, pdl) : launch_gemm_cfg<128, 0, 1>(tmA, tmB, tmC, a, st, pdl);
   if (BN == 256) return bf ? launch_gemm_cfg<256, 1, 0>(tmA, tmB, tmC, a, st, pdl) : launch_gemm_cfg<256, 0, 0>(tmA, tmB, tmC, a, st, pdl);
   if (BN == 128) return bf ? launch_gemm_cfg<128, 1, 0>(tmA, tmB, tmC, a, st, pdl) : launch_gemm_cfg<128, 0, 0>(tmA, tmB, tmC, a, st, pdl);
