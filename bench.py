@@ -747,9 +747,9 @@ def main():
             rf['peak_source'] = pk['source']
         if fused and args.workload == 'darcy241' and args.precision == 'f16':
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_apply_tc launch, ncu --set full capture of this
-            # command (profiles/r1g_apply_full.md): 52.86 GB + 4.18 GB; algorithmic bytes per launch = E * 2052 B
-            rf_conv['traffic'] = 57.20e9
-            rf_conv['traffic_source'] = 'profiles/r2e_k_apply_tc_full.md (per launch: 52.85 GB read + 4.35 GB written; algorithmic %.2f GB per launch)' % (E * (Kp * es + 4) / 1e9)
+            # command (profiles/r2r_k_apply_tc_full.md); algorithmic bytes per launch = E * 2052 B
+            rf_conv['traffic'] = 56.86e9
+            rf_conv['traffic_source'] = 'profiles/r2r_k_apply_tc_full.md (per launch: 52.50 GB read + 4.36 GB written; algorithmic %.2f GB per launch)' % (E * (Kp * es + 4) / 1e9)
         dominant = rf_conv if conv_ms >= gemm_ms else rf_gemm
         f_alg = 2.0 * (6 * kw + kw * kw + kw * w * w + w * w)    # SURVEY 8(d), reference formulation A
         b_alg = 16 + 24 + 4.0 * 2 * w * N / E
