@@ -45,7 +45,7 @@ _BWD_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_WS_BYTES', str(2 << 30)))  #
 # tensor-core backward: per-application workspace (dY of a source batch: 7.6 GB covers 241^2 in one batch) and the
 # per-batch buffers of the deferred pass through the hidden layers
 _BWD_APPLY_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_APPLY_WS_BYTES', str(9 << 30)))
-_BWD_MLP_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_MLP_WS_BYTES', str(6 << 30)))
+_BWD_MLP_WS_BYTES = int(os.environ.get('NNCONV_B200_BWD_MLP_WS_BYTES', str(12 << 30)))   # 1 GiB: +16 ms, 256 MiB: +139 ms per 241^2 step (run r2t)
 _BWD_MODE = os.environ.get('NNCONV_B200_BACKWARD', 'auto')       # auto | tc | fp32
 # training: keep the hidden activations h_1..h_{L-2} of the forward for the backward (2 KB per edge and layer at width
 # 1024: 50 GB at 241^2) instead of recomputing them, when they fit this budget
