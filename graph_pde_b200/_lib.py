@@ -15,6 +15,7 @@ OK = 0
 ABI_VERSION = 2        # include/nnconv_b200.h: NNCONV_B200_ABI_VERSION this binding was written against
 PREC = {'fp32': 0, 'f16': 1, 'fp16': 1, 'bf16': 2, 'f16x2': 3}
 AGGR = {'add': 0, 'mean': 1}
+APPLY_RELU_IN, APPLY_RESIDUAL = 1, 2        # include/nnconv_b200.h NNCONV_APPLY_*
 FLOW = {'source_to_target': 0, 'target_to_source': 1}
 
 # every symbol include/nnconv_b200.h declares (tests/test_cabi_symbols.py checks the .so exports them)
@@ -32,7 +33,7 @@ SYMBOLS = [
     'nnconv_ipc_alloc', 'nnconv_ipc_open', 'nnconv_ipc_close', 'nnconv_ipc_free',
     'nnconv_ball_count', 'nnconv_ball_fill',
     'nnconv_edge_kernels_sizes', 'nnconv_edge_kernels', 'nnconv_apply_edge',
-    'nnconv_edge_acts_sizes', 'nnconv_edge_features_keep',
+    'nnconv_edge_acts_sizes', 'nnconv_edge_features_keep', 'nnconv_apply_ex', 'nnconv_apply_edge_ex',
 ]
 
 
@@ -114,6 +115,8 @@ def lib():
     L.nnconv_edge_kernels_sizes.argtypes = [c_vp, c_vp, P(c_sz)]
     L.nnconv_edge_kernels.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp]
     L.nnconv_apply_edge.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp]
+    L.nnconv_apply_edge_ex.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, ctypes.c_uint, c_vp, c_vp]
+    L.nnconv_apply_ex.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, ctypes.c_uint, c_vp, c_vp, c_sz, c_vp, P(c_i64)]
     L.nnconv_ball_count.argtypes = [c_vp, c_i64, c_vp, c_i64, ctypes.c_double, c_vp, c_vp]
     L.nnconv_ball_fill.argtypes = [c_vp, c_i64, c_vp, c_i64, ctypes.c_double, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp,
                                    c_vp, c_vp]

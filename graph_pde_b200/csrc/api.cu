@@ -357,11 +357,13 @@ int edge_kernels(const Plan* P, const Weights* W, const void* h, void* Kmat, cud
 }
 
 int apply_edge(const Plan* P, const Weights* W, const void* Kmat, const float* x, const float* root, const float* bias,
-               int aggr_mean, float* out, cudaStream_t st) {
-  int s = launch_out_init(x, root, bias, P->N, W->cin, W->cout, out, st);
+               int aggr_mean, float* out, cudaStream_t st, unsigned node_flags) {
+  NNC_REQUIRE(!(node_flags & NNCONV_APPLY_RESIDUAL) || W->cin == W->cout, NNCONV_ERR_ARG,
+              "NNCONV_APPLY_RESIDUAL needs in_channels == out_channels");
+  int s = launch_out_init(x, root, bias, P->N, W->cin, W->cout, out, st, node_flags);
   if (s) return s;
   if (P->E == 0 || P->n_src == 0) return NNCONV_OK;
-  return launch_apply_edge(W->prec, P, W, Kmat, x, aggr_mean, out, st);
+  return launch_apply_edge(W->prec, P, W, Kmat, x, aggr_mean, out, st, node_flags);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -395,15 +397,16 @@ size_t apply_ws_bytes(const Plan* P, const Weights* W, size_t want_y_bytes) {
 }
 
 int apply(const Plan* P, const Weights* W, const void* h, const float* x, const float* root, const float* bias,
-          int aggr_mean, float* out, void* ws, size_t ws_bytes, cudaStream_t st, int64_t* launches) {
+          int aggr_mean, float* out, void* ws, size_t ws_bytes, cudaStream_t st, int64_t* launches, unsigned node_flags) {
   int s;
-  {
+  NNC_REQUIRE(!(node_flags & NNCONV_APPLY_RESIDUAL) || W->cin == W->cout, NNCONV_ERR_ARG,
+              "NNCONV_APPLY_RESIDUAL needs in_channels == out_channels");
+  if (P->E == 0 || P->n_src == 0) {
     ProfScope ps(PK_NODE_PREP, st);
-    s = launch_out_init(x, root, bias, P->N, W->cin, W->cout, out, st);
+    s = launch_out_init(x, root, bias, P->N, W->cin, W->cout, out, st, node_flags);
+    if (s == NNCONV_OK && launches) ++*launches;
+    return s;
   }
-  if (s) return s;
-  if (launches) ++*launches;
-  if (P->E == 0 || P->n_src == 0) return NNCONV_OK;
   const bool tc = tc_shapes_supported(W);
   NNC_REQUIRE(tc || W->prec == PREC_FP32, NNCONV_ERR_UNSUPPORTED,
               "shape not supported by the tensor-core path (out=%d, K=%d); use precision fp32", W->cout, W->K);
@@ -416,12 +419,40 @@ int apply(const Plan* P, const Weights* W, const void* h, const float* x, const 
   float* xs = reinterpret_cast<float*>(base + L.off_xs);
   void* Y = base + L.off_Y;
   int64_t nodes_cap = static_cast<int64_t>((ws_bytes - L.fixed_bytes) / L.per_node);
-  {
-    ProfScope ps(PK_NODE_PREP, st);
-    s = launch_src_prep(W->prec, x, P->src_nodes, P->n_src, W->cin, W->cin_p, W->cout, W->B3, Xc, cvec, xs, st);
+  const Options& opt = options();
+  // fused persistent kernel (below): its batch geometry is needed here because the node-prep launch also clears its flags
+  const bool no_fuse_env = opt.no_fuse != 0 && !W->split;      // measurement / debugging knob
+  bool fused = W->prec != PREC_FP32 && !no_fuse_env && apply_fused_supported(W);
+  int ring = opt.ring;   // measured (run22): with dynamic unit scheduling 3 x 128 sources (48 MB at out=64, Kp=1024) is best
+  int64_t nb = 0;
+  if (fused) {
+    if (opt.ring_deep && nodes_cap / 128 > ring) ring = nodes_cap / 128 < 16 ? static_cast<int>(nodes_cap / 128) : 16;
+    if (nodes_cap < ring) ring = nodes_cap >= 2 ? static_cast<int>(nodes_cap) : 1;
+    nb = nodes_cap / ring;
+    if (nb >= 128) nb = nb / 128 * 128;
+    if (nb > P->n_src) nb = P->n_src;
+    fused = ceil_div64(P->n_src, nb) <= kMaxPipeBatches && ring >= 2;
   }
-  if (s) return s;
-  if (launches) ++*launches;
+  int* flags = reinterpret_cast<int*>(base + L.off_flags);
+  if (fused) {
+    ProfScope ps(PK_NODE_PREP, st);
+    s = launch_node_prep(W->prec, x, root, bias, P->N, out, P->src_nodes, P->n_src, W->cin, W->cin_p, W->cout, W->B3, Xc,
+                         cvec, xs, flags, kMaxPipeBatches, static_cast<int>(ceil_div64(P->n_src, nb)), st, node_flags);
+    if (s) return s;
+    if (launches) ++*launches;
+  } else {
+    {
+      ProfScope ps(PK_NODE_PREP, st);
+      s = launch_out_init(x, root, bias, P->N, W->cin, W->cout, out, st, node_flags);
+    }
+    if (s) return s;
+    {
+      ProfScope ps(PK_NODE_PREP, st);
+      s = launch_src_prep(W->prec, x, P->src_nodes, P->n_src, W->cin, W->cin_p, W->cout, W->B3, Xc, cvec, xs, st, node_flags);
+    }
+    if (s) return s;
+    if (launches) *launches += 2;
+  }
   // tile_ptr lives on the device; tile ranges per batch come from the host mirror kept in the plan handle
   const int* h_tile_ptr = P->h_tile_ptr;
   const int NY = W->cout * W->Kp;
@@ -451,29 +482,18 @@ int apply(const Plan* P, const Weights* W, const void* h, const float* x, const 
 
   // Tensor-core path, default: ONE persistent kernel per application (apply_tc.cu) in which every CTA runs
   // the Y GEMM pipeline and the contraction pipeline concurrently over a ring of L2-resident Y batches.
-  const Options& opt = options();
-  const bool no_fuse_env = opt.no_fuse != 0 && !W->split;      // measurement / debugging knob
-  if (!no_fuse_env && apply_fused_supported(W)) {
-    int ring = opt.ring;   // measured (run22): with dynamic unit scheduling 3 x 128 sources (48 MB at out=64, Kp=1024) is best
-    if (nodes_cap < ring) ring = nodes_cap >= 2 ? static_cast<int>(nodes_cap) : 1;
-    int64_t nb = nodes_cap / ring;
-    if (nb >= 128) nb = nb / 128 * 128;
-    if (nb > P->n_src) nb = P->n_src;
-    if (ceil_div64(P->n_src, nb) <= kMaxPipeBatches && ring >= 2) {
-      int* flags = reinterpret_cast<int*>(base + L.off_flags);
-      NNC_CHECK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * 5 * kMaxPipeBatches, st));
-      {
-        ProfScope ps(PK_APPLY_FUSED, st);
-        s = launch_apply_tc(W->prec, P, W, h, Xc, Y, static_cast<int>(nb), ring, cvec, xs, aggr_mean, out, flags,
-                            kMaxPipeBatches, st);
-      }
-      if (s == NNCONV_OK) {
-        if (launches) ++*launches;
-        return NNCONV_OK;
-      }
-      // the driver cannot co-schedule one CTA per SM (MPS / green-context partition): per-batch kernels below
-      if (s != kApplyCannotCoSchedule) return s;
+  if (fused) {
+    {
+      ProfScope ps(PK_APPLY_FUSED, st);
+      s = launch_apply_tc(W->prec, P, W, h, Xc, Y, static_cast<int>(nb), ring, cvec, xs, aggr_mean, out, flags,
+                          kMaxPipeBatches, st);
     }
+    if (s == NNCONV_OK) {
+      if (launches) ++*launches;
+      return NNCONV_OK;
+    }
+    // the driver cannot co-schedule one CTA per SM (MPS / green-context partition): per-batch kernels below
+    if (s != kApplyCannotCoSchedule) return s;
   }
   NNC_REQUIRE(!W->split, NNCONV_ERR_UNSUPPORTED,
               "precision f16x2 runs in the fused persistent kernel only (shape or workspace not supported)");
@@ -493,7 +513,6 @@ int apply(const Plan* P, const Weights* W, const void* h, const float* x, const 
   if (n_batches > kMaxPipeBatches) {   // keep the flag table bounded: grow batches past the L2 target
     NNC_REQUIRE(false, NNCONV_ERR_WORKSPACE, "apply: workspace too small for %lld source batches", (long long)n_batches);
   }
-  int* flags = reinterpret_cast<int*>(base + L.off_flags);
   int* cntY = flags;
   int* cntC = flags + kMaxPipeBatches;
   int* okY = flags + 2 * kMaxPipeBatches;
@@ -725,6 +744,16 @@ int nnconv_apply_edge(const nnconv_plan_t* plan, const nnconv_weights_t* w, cons
   return apply_edge(&plan->p, &w->w, kmat, x, root, bias, aggr == NNCONV_AGGR_MEAN, out, static_cast<cudaStream_t>(stream));
 }
 
+int nnconv_apply_edge_ex(const nnconv_plan_t* plan, const nnconv_weights_t* w, const void* kmat, const float* x,
+                         const float* root, const float* bias, int aggr, unsigned flags, float* out, void* stream) {
+  NNC_REQUIRE(plan && w && x && out && (kmat || plan->p.E == 0), NNCONV_ERR_ARG, "null pointer");
+  NNC_REQUIRE(aggr == NNCONV_AGGR_ADD || aggr == NNCONV_AGGR_MEAN, NNCONV_ERR_UNSUPPORTED, "aggr must be add or mean");
+  NNC_REQUIRE((flags & ~(NNCONV_APPLY_RELU_IN | NNCONV_APPLY_RESIDUAL)) == 0, NNCONV_ERR_ARG, "unknown apply flag");
+  NNC_REQUIRE(x != out, NNCONV_ERR_ARG, "out must not alias x");
+  return apply_edge(&plan->p, &w->w, kmat, x, root, bias, aggr == NNCONV_AGGR_MEAN, out, static_cast<cudaStream_t>(stream),
+                    flags);
+}
+
 int nnconv_apply_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t want_y_bytes, size_t* ws_bytes) {
   NNC_REQUIRE(plan && w && ws_bytes, NNCONV_ERR_ARG, "null pointer");
   *ws_bytes = apply_ws_bytes(&plan->p, &w->w, want_y_bytes);
@@ -739,6 +768,18 @@ int nnconv_apply(const nnconv_plan_t* plan, const nnconv_weights_t* w, const voi
               "aggr must be add (0) or mean (1); 'max' is used by no call site of the reference and is not built");
   return apply(&plan->p, &w->w, h, x, root, bias, aggr == NNCONV_AGGR_MEAN, out, ws, ws_bytes,
                static_cast<cudaStream_t>(stream), launches);
+}
+
+int nnconv_apply_ex(const nnconv_plan_t* plan, const nnconv_weights_t* w, const void* h, const float* x,
+                    const float* root, const float* bias, int aggr, unsigned flags, float* out, void* ws, size_t ws_bytes,
+                    void* stream, int64_t* launches) {
+  NNC_REQUIRE(plan && w && x && out && (h || plan->p.E == 0), NNCONV_ERR_ARG, "null pointer");
+  NNC_REQUIRE(aggr == NNCONV_AGGR_ADD || aggr == NNCONV_AGGR_MEAN, NNCONV_ERR_UNSUPPORTED,
+              "aggr must be add (0) or mean (1); 'max' is used by no call site of the reference and is not built");
+  NNC_REQUIRE((flags & ~(NNCONV_APPLY_RELU_IN | NNCONV_APPLY_RESIDUAL)) == 0, NNCONV_ERR_ARG, "unknown apply flag");
+  NNC_REQUIRE(x != out, NNCONV_ERR_ARG, "out must not alias x");
+  return apply(&plan->p, &w->w, h, x, root, bias, aggr == NNCONV_AGGR_MEAN, out, ws, ws_bytes,
+               static_cast<cudaStream_t>(stream), launches, flags);
 }
 
 int nnconv_backward_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t want_bytes, size_t* ws_bytes) {

@@ -23,10 +23,15 @@ int launch_edge_layer1(int prec, const float* edge_attr, const int* perm, int64_
 int launch_build_a1(int prec, const float* edge_attr, const int* perm, int64_t e_begin, int64_t e_count, int k_in,
                     void* A1, cudaStream_t st);
 int launch_w1aug(int prec, const float* W1, const float* b1, int k1, int kp1, int k_in, void* dst, cudaStream_t st);
+// node_flags: NNCONV_APPLY_RELU_IN (1) = x holds pre-activations, read max(x, 0); NNCONV_APPLY_RESIDUAL (2) = add the
+// input row to the output row (cin == cout)
 int launch_out_init(const float* x, const float* root, const float* bias, int64_t N, int cin, int cout, float* out,
-                    cudaStream_t st);
+                    cudaStream_t st, unsigned node_flags = 0);
 int launch_src_prep(int prec, const float* x, const int* src_nodes, int S, int cin, int cin_p, int cout,
-                    const float* B3, void* Xc, float* cvec, float* xs, cudaStream_t st);
+                    const float* B3, void* Xc, float* cvec, float* xs, cudaStream_t st, unsigned node_flags = 0);
+int launch_node_prep(int prec, const float* x, const float* root, const float* bias, int64_t N, float* out,
+                     const int* src_nodes, int S, int cin, int cin_p, int cout, const float* B3, void* Xc, float* cvec,
+                     float* xs, int* flags, int flags_stride, int n_batches, cudaStream_t st, unsigned node_flags);
 int launch_sgemm_store(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,
                        int K, const float* bias_relu, cudaStream_t st);
 int launch_sgemm_scatter(const Plan* P, const float* h, int Kp, const float* Y, int cout, int tile_begin,
@@ -68,7 +73,7 @@ int launch_gemm_tc(int prec, const void* A_base, int64_t a_rows_total, int64_t a
 // ---- per-edge kernel matrices (formulation B, for graphs with few out-edges per source): K_e = W_L h_e + b_L once per
 // (edge_attr, parameters), then out[dst] += x_src . K_e per application (kernels_simt.cu)
 int launch_apply_edge(int prec, const Plan* P, const Weights* W, const void* Kmat, const float* x, int aggr_mean, float* out,
-                      cudaStream_t st);
+                      cudaStream_t st, unsigned node_flags = 0);
 
 // ---- gemm_tn.cu (tcgen05, MN-major operands): C[M, N] fp32 += alpha * sum_{r<R} A[r, a_col0 + m] * B[r, b_col0 + n]
 // (A: [R, lda], B: [R, ldb] 16-bit row-major; C accumulates with fp32 atomics, the caller zero-initialises it)

@@ -238,23 +238,37 @@ __global__ void k_w1aug(const float* __restrict__ W1, const float* __restrict__ 
   dst[idx] = cvt<T>(out);
 }
 
-// out[n, o] = bias[o] + sum_i x[n, i] root[i, o]   (graph-neural-operator/nn_conv.py:277-282), or 0
-__global__ void k_out_init(const float* __restrict__ x, const float* __restrict__ root, const float* __restrict__ bias,
-                           int64_t N, int cin, int cout, float* __restrict__ out) {
-  extern __shared__ float sx[];   // [nodes_per_block][cin]
+// out[n, o] = bias[o] + sum_i x[n, i] root[i, o]   (graph-neural-operator/nn_conv.py:277-282), or 0.
+// node_flags (nnconv_b200.h NNCONV_APPLY_*): RELU_IN reads max(x, 0) -- the caller hands over the PRE-activation of the
+// previous layer -- and RESIDUAL (cin == cout) adds that input row to the output row, so that one V-cycle step
+// x <- relu(x + conv(x))  (multipole-graph-neural-operator/neurips1_MGKN.py:76) needs no elementwise kernel of its own.
+__device__ __forceinline__ void out_init_rows(const float* __restrict__ x, const float* __restrict__ root,
+                                              const float* __restrict__ bias, int64_t N, int cin, int cout,
+                                              float* __restrict__ out, unsigned node_flags, int64_t row_block, float* sx) {
   const int npb = blockDim.y;
-  int64_t n = static_cast<int64_t>(blockIdx.x) * npb + threadIdx.y;
+  int64_t n = row_block * npb + threadIdx.y;
   float* myx = sx + threadIdx.y * cin;
-  if (root != nullptr && n < N)
-    for (int i = threadIdx.x; i < cin; i += blockDim.x) myx[i] = x[n * cin + i];
+  const bool relu_in = (node_flags & 1u) != 0, residual = (node_flags & 2u) != 0;
+  if ((root != nullptr || residual) && n < N)
+    for (int i = threadIdx.x; i < cin; i += blockDim.x) {
+      const float v = x[n * cin + i];
+      myx[i] = relu_in ? fmaxf(v, 0.f) : v;
+    }
   __syncthreads();
   if (n >= N) return;
   for (int o = threadIdx.x; o < cout; o += blockDim.x) {
     float acc = bias ? bias[o] : 0.f;
+    if (residual) acc += myx[o];
     if (root)
       for (int i = 0; i < cin; ++i) acc = fmaf(myx[i], root[i * cout + o], acc);
     out[n * cout + o] = acc;
   }
+}
+
+__global__ void k_out_init(const float* __restrict__ x, const float* __restrict__ root, const float* __restrict__ bias,
+                           int64_t N, int cin, int cout, float* __restrict__ out, unsigned node_flags) {
+  extern __shared__ float sx[];   // [nodes_per_block][cin]
+  out_init_rows(x, root, bias, N, cin, cout, out, node_flags, blockIdx.x, sx);
 }
 
 // per compact source c: Xc[c, :] = x[src_nodes[c], :] / xs[c] (converted, zero padded to cin_p),
@@ -264,17 +278,21 @@ __global__ void k_out_init(const float* __restrict__ x, const float* __restrict_
 // and the epilogue multiplies the accumulator by xs[c].  Without it node features beyond the fp16 range
 // (65504; an untrained MGKN V-cycle reaches 5e5 after 4 depth iterations) turned into inf/NaN.
 // SPLIT (PREC_F16X2): Xc row = [hi | hi | lo] of the normalised row (3 * cin_p columns).
-template <typename T, int SPLIT = 0>
-__global__ void k_src_prep(const float* __restrict__ x, const int* __restrict__ src_nodes, int S, int cin, int cin_p,
-                           int cout, const float* __restrict__ B3, T* __restrict__ Xc, float* __restrict__ cvec,
-                           float* __restrict__ xs) {
-  extern __shared__ float sx[];
+template <typename T, int SPLIT>
+__device__ __forceinline__ void src_prep_rows(const float* __restrict__ x, const int* __restrict__ src_nodes, int S, int cin,
+                                              int cin_p, int cout, const float* __restrict__ B3, T* __restrict__ Xc,
+                                              float* __restrict__ cvec, float* __restrict__ xs, unsigned node_flags,
+                                              int row_block, float* sx) {
   const int npb = blockDim.y;
-  int c = blockIdx.x * npb + threadIdx.y;
+  int c = row_block * npb + threadIdx.y;
   float* myx = sx + threadIdx.y * cin;
   int n = c < S ? src_nodes[c] : 0;
+  const bool relu_in = (node_flags & 1u) != 0;
   if (c < S)
-    for (int i = threadIdx.x; i < cin; i += blockDim.x) myx[i] = x[static_cast<int64_t>(n) * cin + i];
+    for (int i = threadIdx.x; i < cin; i += blockDim.x) {
+      const float v = x[static_cast<int64_t>(n) * cin + i];
+      myx[i] = relu_in ? fmaxf(v, 0.f) : v;
+    }
   __syncthreads();
   if (c >= S) return;
   float inv = 1.f;
@@ -310,6 +328,39 @@ __global__ void k_src_prep(const float* __restrict__ x, const int* __restrict__ 
     for (int i = 0; i < cin; ++i) acc = fmaf(myx[i], B3[i * cout + o], acc);
     cvec[static_cast<int64_t>(c) * cout + o] = acc;
   }
+}
+
+template <typename T, int SPLIT = 0>
+__global__ void k_src_prep(const float* __restrict__ x, const int* __restrict__ src_nodes, int S, int cin, int cin_p,
+                           int cout, const float* __restrict__ B3, T* __restrict__ Xc, float* __restrict__ cvec,
+                           float* __restrict__ xs, unsigned node_flags) {
+  extern __shared__ float sx[];
+  src_prep_rows<T, SPLIT>(x, src_nodes, S, cin, cin_p, cout, B3, Xc, cvec, xs, node_flags, blockIdx.x, sx);
+}
+
+// One launch for everything a fused application needs before its persistent kernel: blocks [0, g_out) initialise the
+// output rows, blocks [g_out, g_out + g_src) prepare the source rows, and the first threads of the grid clear the batch
+// flags of the application (cntY / cntC / okY / okC [n_batches] at stride flags_stride, and the unit counter) -- in the
+// launch-bound MGKN regime (52 dependent applications per forward) each removed graph node is ~5 us of the chain.
+template <typename T, int SPLIT = 0>
+__global__ void k_node_prep(const float* __restrict__ x, const float* __restrict__ root, const float* __restrict__ bias,
+                            int64_t N, float* __restrict__ out, int g_out, const int* __restrict__ src_nodes, int S, int cin,
+                            int cin_p, int cout, const float* __restrict__ B3, T* __restrict__ Xc, float* __restrict__ cvec,
+                            float* __restrict__ xs, int* __restrict__ flags, int flags_stride, int n_batches,
+                            unsigned node_flags) {
+  extern __shared__ float sx[];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * (blockDim.x * blockDim.y) + tid;
+  if (gid < n_batches) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) flags[j * flags_stride + gid] = 0;
+  }
+  if (gid == 0) flags[4 * flags_stride] = 0;
+  if (static_cast<int>(blockIdx.x) < g_out)
+    out_init_rows(x, root, bias, N, cin, cout, out, node_flags, blockIdx.x, sx);
+  else
+    src_prep_rows<T, SPLIT>(x, src_nodes, S, cin, cin_p, cout, B3, Xc, cvec, xs, node_flags,
+                            static_cast<int>(blockIdx.x) - g_out, sx);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -422,7 +473,7 @@ template <typename T2>
 __global__ void __launch_bounds__(256)
 k_apply_edge(const T2* __restrict__ Kmat, const float* __restrict__ x, const int* __restrict__ src_nodes,
              const int* __restrict__ group_ptr, const int* __restrict__ dst_sorted, const float* __restrict__ inv_deg,
-             int S, int64_t E, int cin, int cout, float* __restrict__ out) {
+             int S, int64_t E, int cin, int cout, float* __restrict__ out, unsigned node_flags) {
   // one warp per EDGE (sorted position p): parallelism = E warps whatever the degree distribution is (one warp per
   // source serialised the 18-55 edges of MGKN's coarse levels and ran 3x slower than formulation C, run r2i)
   extern __shared__ float sxe[];
@@ -437,7 +488,11 @@ k_apply_edge(const T2* __restrict__ Kmat, const float* __restrict__ x, const int
   }
   float* sx = sxe + warp * cin;
   const int n = __ldg(src_nodes + lo);
-  for (int i = lane; i < cin; i += 32) sx[i] = __ldg(x + static_cast<int64_t>(n) * cin + i);
+  const bool relu_in = (node_flags & 1u) != 0;     // x is a pre-activation (see k_out_init)
+  for (int i = lane; i < cin; i += 32) {
+    const float v = __ldg(x + static_cast<int64_t>(n) * cin + i);
+    sx[i] = relu_in ? fmaxf(v, 0.f) : v;
+  }
   __syncwarp();
   const int half_cout = cout / 2;
   const T2* Kp = Kmat + p * cin * half_cout;
@@ -463,14 +518,18 @@ template <typename T2>
 __global__ void __launch_bounds__(128)
 k_apply_edge_src(const T2* __restrict__ Kmat, const float* __restrict__ x, const int* __restrict__ src_nodes,
                  const int* __restrict__ group_ptr, const int* __restrict__ dst_sorted, const float* __restrict__ inv_deg,
-                 int S, int cin, int cout, float* __restrict__ out) {
+                 int S, int cin, int cout, float* __restrict__ out, unsigned node_flags) {
   extern __shared__ float sxe[];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
   const int c = blockIdx.x * 4 + warp;
   if (c >= S) return;
   float* sx = sxe + warp * cin;
   const int n = src_nodes[c];
-  for (int i = lane; i < cin; i += 32) sx[i] = x[static_cast<int64_t>(n) * cin + i];
+  const bool relu_in = (node_flags & 1u) != 0;
+  for (int i = lane; i < cin; i += 32) {
+    const float v = x[static_cast<int64_t>(n) * cin + i];
+    sx[i] = relu_in ? fmaxf(v, 0.f) : v;
+  }
   __syncwarp();
   const int e0 = group_ptr[c], e1 = group_ptr[c + 1];
   const int half_cout = cout / 2;
@@ -490,6 +549,124 @@ k_apply_edge_src(const T2* __restrict__ Kmat, const float* __restrict__ x, const
       atomicAdd(o, ax * sc);
       atomicAdd(o + 1, ay * sc);
     }
+  }
+}
+
+// ---- 16-byte-load variants of the two kernels above for the shapes the reference's scripts use (in = out = 64 or 32).
+// A K_e row of COUT 16-bit values is LPR = COUT/8 lanes wide, so ONE warp-wide load instruction covers RPI = 256/COUT
+// input channels and an edge needs only CIN/RPI (= 16 at 64 x 64) independent loads per lane, all issued back to back
+// BEFORE the source search / x staging they do not depend on.  The scalar kernels issue 64 dependent-looking 4-byte
+// loads per lane and were latency bound: 23 us per launch for <= 8192 edges, 96 us for the warp-per-source kernel on a
+// 100-source level of the MGKN V-cycle (profiles/r2u_mgkn_forward_launches.md).
+__device__ __forceinline__ void red_add_v4f(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int CIN, int COUT>
+struct EdgeVec {
+  static constexpr int LPR = COUT / 8;     // lanes per K_e row
+  static constexpr int RPI = 32 / LPR;     // input channels per warp-wide load
+  static constexpr int NIT = CIN / RPI;    // loads per lane and edge
+  static_assert(COUT % 8 == 0 && 32 % LPR == 0 && CIN % RPI == 0 && RPI >= 2, "unsupported K_e shape");
+
+  template <typename T2>
+  static __device__ __forceinline__ void load(const T2* __restrict__ Kp, int lane, uint4 (&kv)[NIT]) {
+    const uint4* src = reinterpret_cast<const uint4*>(Kp) + lane;     // row lane / LPR, 16-byte piece lane % LPR
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) kv[it] = __ldg(src + it * 32);   // RPI rows further = 32 pieces further
+  }
+
+  // out row += sc * (x . K_e): every lane accumulates its 8 columns over its rows, the RPI row groups are summed with
+  // shuffles, and lane groups 0 / 1 each add one 16-byte piece of the lane's 8 columns.
+  template <typename T2>
+  static __device__ __forceinline__ void fma_scatter(const uint4 (&kv)[NIT], const float* sx, int lane, float sc,
+                                                     float* __restrict__ orow) {
+    const int r = lane / LPR, q = lane % LPR;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const float xv = sx[it * RPI + r];
+      const T2* h = reinterpret_cast<const T2*>(&kv[it]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 k = cvt2<T2>(h[j]);
+        acc[2 * j] = fmaf(xv, k.x, acc[2 * j]);
+        acc[2 * j + 1] = fmaf(xv, k.y, acc[2 * j + 1]);
+      }
+    }
+#pragma unroll
+    for (int m = LPR; m < 32; m <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], m);
+    }
+    if (r < 2) {
+      const float a0 = r ? acc[4] : acc[0], a1 = r ? acc[5] : acc[1], a2 = r ? acc[6] : acc[2], a3 = r ? acc[7] : acc[3];
+      red_add_v4f(orow + q * 8 + 4 * r, a0 * sc, a1 * sc, a2 * sc, a3 * sc);
+    }
+  }
+};
+
+template <typename T2, int CIN, int COUT>
+__global__ void __launch_bounds__(256)
+k_apply_edge_v(const T2* __restrict__ Kmat, const float* __restrict__ x, const int* __restrict__ src_nodes,
+               const int* __restrict__ group_ptr, const int* __restrict__ dst_sorted, const float* __restrict__ inv_deg,
+               int S, int64_t E, float* __restrict__ out, unsigned node_flags) {
+  using V = EdgeVec<CIN, COUT>;
+  __shared__ float sxe[8 * CIN];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int64_t p = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  if (p >= E) return;
+  uint4 kv[V::NIT];
+  V::template load<T2>(Kmat + p * (CIN * COUT / 2), lane, kv);
+  int lo = 0, hi = S;                       // compact source of edge p: the last c with group_ptr[c] <= p
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(group_ptr + mid) <= p) lo = mid; else hi = mid;
+  }
+  float* sx = sxe + warp * CIN;
+  const int n = __ldg(src_nodes + lo);
+  const bool relu_in = (node_flags & 1u) != 0;
+  for (int i = lane; i < CIN; i += 32) {
+    const float v = __ldg(x + static_cast<int64_t>(n) * CIN + i);
+    sx[i] = relu_in ? fmaxf(v, 0.f) : v;
+  }
+  __syncwarp();
+  const int d = __ldg(dst_sorted + p);
+  const float sc = inv_deg ? __ldg(inv_deg + d) : 1.f;
+  V::template fma_scatter<T2>(kv, sx, lane, sc, out + static_cast<int64_t>(d) * COUT);
+}
+
+template <typename T2, int CIN, int COUT>
+__global__ void __launch_bounds__(128)
+k_apply_edge_src_v(const T2* __restrict__ Kmat, const float* __restrict__ x, const int* __restrict__ src_nodes,
+                   const int* __restrict__ group_ptr, const int* __restrict__ dst_sorted, const float* __restrict__ inv_deg,
+                   int S, float* __restrict__ out, unsigned node_flags) {
+  using V = EdgeVec<CIN, COUT>;
+  __shared__ float sxe[4 * CIN];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int c = blockIdx.x * 4 + warp;
+  if (c >= S) return;
+  const int e0 = group_ptr[c], e1 = group_ptr[c + 1];
+  uint4 kv[V::NIT];
+  if (e0 < e1) V::template load<T2>(Kmat + static_cast<int64_t>(e0) * (CIN * COUT / 2), lane, kv);
+  float* sx = sxe + warp * CIN;
+  const int n = src_nodes[c];
+  const bool relu_in = (node_flags & 1u) != 0;
+  for (int i = lane; i < CIN; i += 32) {
+    const float v = x[static_cast<int64_t>(n) * CIN + i];
+    sx[i] = relu_in ? fmaxf(v, 0.f) : v;
+  }
+  __syncwarp();
+  for (int p = e0; p < e1; ++p) {
+    const int d = dst_sorted[p];
+    const float sc = inv_deg ? inv_deg[d] : 1.f;
+    uint4 cur[V::NIT];
+#pragma unroll
+    for (int it = 0; it < V::NIT; ++it) cur[it] = kv[it];
+    if (p + 1 < e1) V::template load<T2>(Kmat + static_cast<int64_t>(p + 1) * (CIN * COUT / 2), lane, kv);   // next edge in flight
+    V::template fma_scatter<T2>(cur, sx, lane, sc, out + static_cast<int64_t>(d) * COUT);
   }
 }
 
@@ -616,60 +793,105 @@ int launch_w1aug(int prec, const float* W1, const float* b1, int k1, int kp1, in
 }
 
 int launch_out_init(const float* x, const float* root, const float* bias, int64_t N, int cin, int cout, float* out,
-                    cudaStream_t st) {
+                    cudaStream_t st, unsigned node_flags) {
   dim3 b(64, 4);
   unsigned g = (unsigned)ceil_div64(N, b.y);
-  k_out_init<<<g, b, sizeof(float) * b.y * cin, st>>>(x, root, bias, N, cin, cout, out);
+  k_out_init<<<g, b, sizeof(float) * b.y * cin, st>>>(x, root, bias, N, cin, cout, out, node_flags);
   NNC_CHECK_LAUNCH();
   return NNCONV_OK;
 }
 
 int launch_src_prep(int prec, const float* x, const int* src_nodes, int S, int cin, int cin_p, int cout,
-                    const float* B3, void* Xc, float* cvec, float* xs, cudaStream_t st) {
+                    const float* B3, void* Xc, float* cvec, float* xs, cudaStream_t st, unsigned node_flags) {
   if (S <= 0) return NNCONV_OK;
   dim3 b(64, 4);
   unsigned g = (unsigned)ceil_div(S, (int)b.y);
   size_t sm = sizeof(float) * b.y * cin;
   if (prec == PREC_FP32)
-    k_src_prep<float><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3, static_cast<float*>(Xc), cvec, nullptr);
+    k_src_prep<float><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3, static_cast<float*>(Xc), cvec, nullptr,
+                                        node_flags);
   else if (prec == PREC_F16)
-    k_src_prep<__half><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3, static_cast<__half*>(Xc), cvec, xs);
+    k_src_prep<__half><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3, static_cast<__half*>(Xc), cvec, xs,
+                                         node_flags);
   else if (prec == PREC_F16X2)
-    k_src_prep<__half, 1><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3, static_cast<__half*>(Xc), cvec, xs);
+    k_src_prep<__half, 1><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3, static_cast<__half*>(Xc), cvec, xs,
+                                            node_flags);
   else
     k_src_prep<__nv_bfloat16><<<g, b, sm, st>>>(x, src_nodes, S, cin, cin_p, cout, B3,
-                                                static_cast<__nv_bfloat16*>(Xc), cvec, xs);
+                                                static_cast<__nv_bfloat16*>(Xc), cvec, xs, node_flags);
   NNC_CHECK_LAUNCH();
   return NNCONV_OK;
 }
 
-int launch_apply_edge(int prec, const Plan* P, const Weights* W, const void* Kmat, const float* x, int aggr_mean, float* out,
-                      cudaStream_t st) {
-  const int S = P->n_src;
-  if (S <= 0 || P->E <= 0) return NNCONV_OK;
-  const float* inv_deg = aggr_mean ? P->inv_deg : nullptr;
-  if (P->E <= 8 * static_cast<int64_t>(S)) {       // a handful of edges per source: warp per source
-    const unsigned g = (unsigned)ceil_div(S, 4);
-    const size_t sm = sizeof(float) * 4 * W->cin;
-    if (prec == PREC_BF16)
-      k_apply_edge_src<__nv_bfloat162><<<g, 128, sm, st>>>(static_cast<const __nv_bfloat162*>(Kmat), x, P->src_nodes,
-                                                           P->group_ptr, P->dst_sorted, inv_deg, S, W->cin, W->cout, out);
-    else
-      k_apply_edge_src<__half2><<<g, 128, sm, st>>>(static_cast<const __half2*>(Kmat), x, P->src_nodes, P->group_ptr,
-                                                    P->dst_sorted, inv_deg, S, W->cin, W->cout, out);
-    NNC_CHECK_LAUNCH();
-    return NNCONV_OK;
-  }
-  const unsigned g = (unsigned)ceil_div64(P->E, 8);
-  const size_t sm = sizeof(float) * 8 * W->cin;
-  if (prec == PREC_BF16)
-    k_apply_edge<__nv_bfloat162><<<g, 256, sm, st>>>(static_cast<const __nv_bfloat162*>(Kmat), x, P->src_nodes, P->group_ptr,
-                                                     P->dst_sorted, inv_deg, S, P->E, W->cin, W->cout, out);
+// out_init + src_prep + the flag reset of one fused application as ONE launch (16-bit precisions)
+int launch_node_prep(int prec, const float* x, const float* root, const float* bias, int64_t N, float* out,
+                     const int* src_nodes, int S, int cin, int cin_p, int cout, const float* B3, void* Xc, float* cvec,
+                     float* xs, int* flags, int flags_stride, int n_batches, cudaStream_t st, unsigned node_flags) {
+  dim3 b(64, 4);
+  const int g_out = static_cast<int>(ceil_div64(N, b.y));
+  const int g_src = ceil_div(S, (int)b.y);
+  const unsigned g = static_cast<unsigned>(g_out + g_src);
+  size_t sm = sizeof(float) * b.y * cin;
+  if (prec == PREC_F16)
+    k_node_prep<__half><<<g, b, sm, st>>>(x, root, bias, N, out, g_out, src_nodes, S, cin, cin_p, cout, B3,
+                                          static_cast<__half*>(Xc), cvec, xs, flags, flags_stride, n_batches, node_flags);
+  else if (prec == PREC_F16X2)
+    k_node_prep<__half, 1><<<g, b, sm, st>>>(x, root, bias, N, out, g_out, src_nodes, S, cin, cin_p, cout, B3,
+                                             static_cast<__half*>(Xc), cvec, xs, flags, flags_stride, n_batches, node_flags);
+  else if (prec == PREC_BF16)
+    k_node_prep<__nv_bfloat16><<<g, b, sm, st>>>(x, root, bias, N, out, g_out, src_nodes, S, cin, cin_p, cout, B3,
+                                                 static_cast<__nv_bfloat16*>(Xc), cvec, xs, flags, flags_stride, n_batches,
+                                                 node_flags);
   else
-    k_apply_edge<__half2><<<g, 256, sm, st>>>(static_cast<const __half2*>(Kmat), x, P->src_nodes, P->group_ptr, P->dst_sorted,
-                                              inv_deg, S, P->E, W->cin, W->cout, out);
+    return NNCONV_ERR_UNSUPPORTED;
   NNC_CHECK_LAUNCH();
   return NNCONV_OK;
+}
+
+namespace {
+template <typename T2>
+int launch_apply_edge_t(const Plan* P, const Weights* W, const void* Kmat_, const float* x, const float* inv_deg, float* out,
+                        cudaStream_t st, unsigned node_flags) {
+  const T2* Kmat = static_cast<const T2*>(Kmat_);
+  const int S = P->n_src;
+  // warp per SOURCE only when there are enough sources to fill the machine with warps (the 1-D multipole stencils: 8192
+  // ... 2048 sources with 2-4 edges each); a coarse MGKN level (100 sources x 6 edges) runs warp per EDGE
+  const bool per_source = P->E <= 8 * static_cast<int64_t>(S) && S >= 2048;
+  const bool v64 = W->cin == 64 && W->cout == 64, v32 = W->cin == 32 && W->cout == 32;
+  if (per_source) {
+    const unsigned g = (unsigned)ceil_div(S, 4);
+    if (v64)
+      k_apply_edge_src_v<T2, 64, 64><<<g, 128, 0, st>>>(Kmat, x, P->src_nodes, P->group_ptr, P->dst_sorted, inv_deg, S, out,
+                                                        node_flags);
+    else if (v32)
+      k_apply_edge_src_v<T2, 32, 32><<<g, 128, 0, st>>>(Kmat, x, P->src_nodes, P->group_ptr, P->dst_sorted, inv_deg, S, out,
+                                                        node_flags);
+    else
+      k_apply_edge_src<T2><<<g, 128, sizeof(float) * 4 * W->cin, st>>>(Kmat, x, P->src_nodes, P->group_ptr, P->dst_sorted,
+                                                                       inv_deg, S, W->cin, W->cout, out, node_flags);
+  } else {
+    const unsigned g = (unsigned)ceil_div64(P->E, 8);
+    if (v64)
+      k_apply_edge_v<T2, 64, 64><<<g, 256, 0, st>>>(Kmat, x, P->src_nodes, P->group_ptr, P->dst_sorted, inv_deg, S, P->E, out,
+                                                    node_flags);
+    else if (v32)
+      k_apply_edge_v<T2, 32, 32><<<g, 256, 0, st>>>(Kmat, x, P->src_nodes, P->group_ptr, P->dst_sorted, inv_deg, S, P->E, out,
+                                                    node_flags);
+    else
+      k_apply_edge<T2><<<g, 256, sizeof(float) * 8 * W->cin, st>>>(Kmat, x, P->src_nodes, P->group_ptr, P->dst_sorted, inv_deg,
+                                                                   S, P->E, W->cin, W->cout, out, node_flags);
+  }
+  NNC_CHECK_LAUNCH();
+  return NNCONV_OK;
+}
+}  // namespace
+
+int launch_apply_edge(int prec, const Plan* P, const Weights* W, const void* Kmat, const float* x, int aggr_mean, float* out,
+                      cudaStream_t st, unsigned node_flags) {
+  if (P->n_src <= 0 || P->E <= 0) return NNCONV_OK;
+  const float* inv_deg = aggr_mean ? P->inv_deg : nullptr;
+  if (prec == PREC_BF16) return launch_apply_edge_t<__nv_bfloat162>(P, W, Kmat, x, inv_deg, out, st, node_flags);
+  return launch_apply_edge_t<__half2>(P, W, Kmat, x, inv_deg, out, st, node_flags);
 }
 
 int launch_sgemm_store(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int M, int N,

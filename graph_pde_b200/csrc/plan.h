@@ -89,7 +89,8 @@ int edge_features(const Plan* P, const Weights* W, const float* edge_attr, void*
 // one conv application given h_last
 size_t apply_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes);
 int apply(const Plan* P, const Weights* W, const void* h, const float* x, const float* root, const float* bias,
-          int aggr_mean, float* out, void* ws, size_t ws_bytes, cudaStream_t st, int64_t* launches);
+          int aggr_mean, float* out, void* ws, size_t ws_bytes, cudaStream_t st, int64_t* launches,
+          unsigned node_flags = 0);
 
 // tensor-core backward (backward_tc.cu): per application (dx, dW_L, db_L, droot, dbias) and, once per
 // (edge_attr, parameters) for all T applications of a shared conv, the pass through the hidden layers
@@ -108,7 +109,7 @@ size_t edge_kernels_bytes(const Plan* P, const Weights* W);
 bool edge_kernels_supported(const Weights* W);
 int edge_kernels(const Plan* P, const Weights* W, const void* h, void* Kmat, cudaStream_t st);
 int apply_edge(const Plan* P, const Weights* W, const void* Kmat, const float* x, const float* root, const float* bias,
-               int aggr_mean, float* out, cudaStream_t st);
+               int aggr_mean, float* out, cudaStream_t st, unsigned node_flags = 0);
 
 // backward of one application (fp32 CUDA-core path), backward.cu
 size_t backward_ws_bytes(const Plan* P, const Weights* W, size_t want_bytes);

@@ -12,11 +12,16 @@ scripts so that their checkpoints / training loops carry over:
 Only the conv applications run in the CUDA library; the pointwise lifts / projections (fc*) stay
 torch.nn.Linear exactly as in the reference (they are not on the hot path).
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn.functional as F
 
 from .nn_conv import NNConv, NNConv_old
+
+# NNCONV_B200_FUSED_STEPS=0: KernelInduced inference runs the reference's op sequence (conv, add, ReLU as separate kernels)
+_FUSED_STEPS = os.environ.get('NNCONV_B200_FUSED_STEPS', '1') != '0'
 
 
 class DenseNet(torch.nn.Module):
@@ -115,16 +120,34 @@ class KernelInduced(_VCycleBase):
         ei_m, ea_m = data.edge_index_mid, data.edge_attr_mid
         ei_u, ea_u = data.edge_index_up, data.edge_attr_up
         x = self.fc_in(data.x)
-        for _ in range(self.depth):
-            for l in range(self.level - 1):                                   # downward (:74-76)
-                a, b = r_down[l]
-                x = F.relu(x + self.conv_down_list[l](x, ei_d[:, a:b], ea_d[a:b, :]))
-            for l in reversed(range(self.level)):                             # upward (:79-84)
-                a, b = r_mid[l]
-                x = F.relu(x + self.conv_list[l](x, ei_m[:, a:b], ea_m[a:b, :]))
-                if l > 0:
-                    a, b = r_up[l - 1]
-                    x = F.relu(x + self.conv_up_list[l - 1](x, ei_u[:, a:b], ea_u[a:b, :]))
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if _FUSED_STEPS and not needs_grad:
+            # inference: the 13 * depth dependent steps  x <- relu(x + conv(x))  chained on pre-activations, ReLU and
+            # residual inside each application's node-prep launch (NNConv_old.residual_step) -- 2 launches per step
+            # instead of 5-6 in a chain that is launch-latency bound
+            z, act = x, False
+            for _ in range(self.depth):
+                for l in range(self.level - 1):
+                    a, b = r_down[l]
+                    z, act = self.conv_down_list[l].residual_step(z, ei_d[:, a:b], ea_d[a:b, :], relu_in=act), True
+                for l in reversed(range(self.level)):
+                    a, b = r_mid[l]
+                    z, act = self.conv_list[l].residual_step(z, ei_m[:, a:b], ea_m[a:b, :], relu_in=act), True
+                    if l > 0:
+                        a, b = r_up[l - 1]
+                        z, act = self.conv_up_list[l - 1].residual_step(z, ei_u[:, a:b], ea_u[a:b, :], relu_in=act), True
+            x = F.relu(z) if act else z
+        else:
+            for _ in range(self.depth):
+                for l in range(self.level - 1):                                   # downward (:74-76)
+                    a, b = r_down[l]
+                    x = F.relu(x + self.conv_down_list[l](x, ei_d[:, a:b], ea_d[a:b, :]))
+                for l in reversed(range(self.level)):                             # upward (:79-84)
+                    a, b = r_mid[l]
+                    x = F.relu(x + self.conv_list[l](x, ei_m[:, a:b], ea_m[a:b, :]))
+                    if l > 0:
+                        a, b = r_up[l - 1]
+                        x = F.relu(x + self.conv_up_list[l - 1](x, ei_u[:, a:b], ea_u[a:b, :]))
         x = F.relu(self.fc_out1(x[:self.points[0]]))
         return self.fc_out2(x)
 

@@ -477,7 +477,7 @@ class NNConv_old(torch.nn.Module):
         self._k_cache = (h, kmat)
         return kmat
 
-    def _apply_impl(self, plan, prepared, h, x32):
+    def _apply_impl(self, plan, prepared, h, x32, flags=0):
         L = _lib.lib()
         dev = x32.device
         kmat = self._edge_kernels(plan, prepared, h)
@@ -485,8 +485,8 @@ class NNConv_old(torch.nn.Module):
             out = torch.empty(x32.size(0), self.out_channels, dtype=torch.float32, device=dev)
             root = self.root.detach().contiguous().float() if self.root is not None else None
             bias = self.bias.detach().contiguous().float() if self.bias is not None else None
-            _lib.check(L.nnconv_apply_edge(plan.handle, prepared.handle, _ptr(kmat), _ptr(x32), _ptr(root), _ptr(bias),
-                                           _lib.AGGR[self.aggr], _ptr(out), _stream_ptr(dev)))
+            _lib.check(L.nnconv_apply_edge_ex(plan.handle, prepared.handle, _ptr(kmat), _ptr(x32), _ptr(root), _ptr(bias),
+                                              _lib.AGGR[self.aggr], flags, _ptr(out), _stream_ptr(dev)))
             stats['launches'] += 2
             stats['applies'] += 1
             return out
@@ -497,19 +497,35 @@ class NNConv_old(torch.nn.Module):
         root = self.root.detach().contiguous().float() if self.root is not None else None
         bias = self.bias.detach().contiguous().float() if self.bias is not None else None
         n_l = ctypes.c_int64(0)
-        _lib.check(L.nnconv_apply(plan.handle, prepared.handle, _ptr(h), _ptr(x32), _ptr(root), _ptr(bias),
-                                  _lib.AGGR[self.aggr], _ptr(out), _ptr(ws), ws_b.value, _stream_ptr(dev),
-                                  ctypes.byref(n_l)))
+        _lib.check(L.nnconv_apply_ex(plan.handle, prepared.handle, _ptr(h), _ptr(x32), _ptr(root), _ptr(bias),
+                                     _lib.AGGR[self.aggr], flags, _ptr(out), _ptr(ws), ws_b.value, _stream_ptr(dev),
+                                     ctypes.byref(n_l)))
         stats['launches'] += n_l.value
         stats['applies'] += 1
         return out
 
-    def _forward_impl(self, x, edge_index, pseudo):
+    def _forward_impl(self, x, edge_index, pseudo, flags=0):
         self._check_inputs(x, edge_index, pseudo)
         with torch.cuda.device(x.device):
             x32 = x.detach().contiguous().float()
             plan, prepared, _, h = self._prepare(x32, edge_index, pseudo)
-            return self._apply_impl(plan, prepared, h, x32)
+            return self._apply_impl(plan, prepared, h, x32, flags)
+
+    def residual_step(self, z, edge_index, edge_attr, relu_in=True):
+        """One V-cycle step ``x <- relu(x + conv(x))`` (multipole-graph-neural-operator/neurips1_MGKN.py:76,81,84) on
+        PRE-activations, inference only: with ``x = relu(z)`` (``x = z`` if not ``relu_in``) returns
+        ``z' = x + conv(x)``; the caller chains ``z'`` into the next step and applies the last ReLU itself.  The ReLU
+        and the residual live in the node-prep launch of the application (``nnconv_apply_ex``), so a chain of steps
+        has no elementwise kernels between its applications."""
+        if self.in_channels != self.out_channels:
+            raise ValueError('residual_step needs in_channels == out_channels')
+        if torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise RuntimeError('residual_step is a forward-only path: call it under torch.no_grad()')
+        if self.aggr == 'max':
+            raise NotImplementedError("aggr='max' is used by no call site of the reference and is not built")
+        pseudo = edge_attr.unsqueeze(-1) if edge_attr.dim() == 1 else edge_attr
+        flags = _lib.APPLY_RESIDUAL | (_lib.APPLY_RELU_IN if relu_in else 0)
+        return self._forward_impl(z, edge_index, pseudo, flags)
 
     # -- tensor-core training path ----------------------------------------------------------------------
     def _train_state(self, x, edge_index, pseudo):

@@ -130,6 +130,9 @@ int nnconv_edge_kernels_sizes(const nnconv_plan_t* plan, const nnconv_weights_t*
 int nnconv_edge_kernels(const nnconv_plan_t* plan, const nnconv_weights_t* w, const void* h, void* kmat, void* stream);
 int nnconv_apply_edge(const nnconv_plan_t* plan, const nnconv_weights_t* w, const void* kmat, const float* x,
                       const float* root, const float* bias, int aggr, float* out, void* stream);
+/* nnconv_apply_edge with the NNCONV_APPLY_* flags of nnconv_apply_ex (below). */
+int nnconv_apply_edge_ex(const nnconv_plan_t* plan, const nnconv_weights_t* w, const void* kmat, const float* x,
+                         const float* root, const float* bias, int aggr, unsigned flags, float* out, void* stream);
 
 /* ---- one NNConv application: gather + last Linear + per-edge contraction + scatter + root + bias --- */
 int nnconv_apply_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, size_t want_y_bytes, size_t* ws_bytes);
@@ -137,6 +140,19 @@ int nnconv_apply_sizes(const nnconv_plan_t* plan, const nnconv_weights_t* w, siz
 int nnconv_apply(const nnconv_plan_t* plan, const nnconv_weights_t* w, const void* h, const float* x,
                  const float* root, const float* bias, int aggr, float* out, void* ws, size_t ws_bytes, void* stream,
                  int64_t* launches /*nullable*/);
+
+/* One V-cycle step  x <- relu(x + conv(x))  (multipole-graph-neural-operator/neurips1_MGKN.py:76,81,84) without
+ * elementwise kernels between the 52 dependent applications of a forward: the caller keeps the PRE-activation
+ *   z_{k+1} = relu(z_k) + conv(relu(z_k))
+ * and applies the last ReLU itself.  flags:
+ *   NNCONV_APPLY_RELU_IN   x holds pre-activations; every read of x (gather, root term, residual) is max(x, 0)
+ *   NNCONV_APPLY_RESIDUAL  out = (relu?)(x) + conv(...)   (in_channels == out_channels; out must not alias x)
+ * flags = 0 is exactly nnconv_apply.  Forward only. */
+#define NNCONV_APPLY_RELU_IN 1u
+#define NNCONV_APPLY_RESIDUAL 2u
+int nnconv_apply_ex(const nnconv_plan_t* plan, const nnconv_weights_t* w, const void* h, const float* x,
+                    const float* root, const float* bias, int aggr, unsigned flags, float* out, void* ws, size_t ws_bytes,
+                    void* stream, int64_t* launches /*nullable*/);
 
 /* ---- backward of one application (what autograd generates for nn_conv.py:267-282 + utilities.py:223-227):
  * grad_x [N,in], grad_W[l] / grad_b[l] in the torch.nn.Linear layouts of the edge MLP, grad_root [in,out],

@@ -47,6 +47,14 @@ def main():
     edge_apps = depth * (g.edge_index_mid.size(1) + g.edge_index_down.size(1) + g.edge_index_up.size(1))
     with torch.no_grad():
         out = model(g)
+        if os.environ.get('MGKN_PROFILE'):       # ncu --profile-from-start off: the launches of ONE eager forward
+            model(g)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
+            model(g)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+            return
         t_eager = timed(lambda: model(g), 20)
         print('this library, eager      : %8.3f ms  %.3e edge-apps/s' % (t_eager, edge_apps / t_eager * 1e3))
         try:

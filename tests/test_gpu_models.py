@@ -44,10 +44,17 @@ def test_kernelnn_full_forward_cfg1(precision):
     assert rel_err(out, t(g['model_out'])) < TOL[precision]
 
 
+@pytest.mark.parametrize('steps', ['fused', 'plain'])
 @pytest.mark.parametrize('variant', ['neurips1', 'general'])
 @pytest.mark.parametrize('precision', ['f16', 'fp32'])
-def test_mgkn_vcycle(variant, precision):
+def test_mgkn_vcycle(variant, precision, steps, monkeypatch):
+    """`steps`: KernelInduced inference chains `residual_step` on pre-activations ('fused', the default) or runs the
+    reference's conv / add / ReLU sequence ('plain', NNCONV_B200_FUSED_STEPS=0); both against the reference's output."""
+    from graph_pde_b200 import models
     from graph_pde_b200.models import KernelInduced, MKGN
+    if steps == 'plain' and variant != 'neurips1':
+        pytest.skip('only KernelInduced has the fused step chain')
+    monkeypatch.setattr(models, '_FUSED_STEPS', steps == 'fused')
     g = np.load(os.path.join(GOLDEN, 'g4_mgkn_vcycle.npz'))
     pts = [int(p) for p in g['points']]
     cls = KernelInduced if variant == 'neurips1' else MKGN

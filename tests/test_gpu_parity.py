@@ -303,3 +303,73 @@ def test_low_out_degree_graph_uses_per_edge_kernel_matrices(dev, precision, edge
     finally:
         nn_conv._EDGE_KERNELS = old
     assert rel_err(out_b, out_c) < 2 * TOL[precision]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('precision', ['f16', 'bf16', 'f16x2', 'fp32'])
+@pytest.mark.parametrize('flags', ['', 'root', 'root+bias'])
+def test_residual_step_equals_conv_add_on_preactivations(dev, precision, flags, edge_kernel_mode):
+    """`residual_step` (nnconv_apply_ex / nnconv_apply_edge_ex with NNCONV_APPLY_RELU_IN | NNCONV_APPLY_RESIDUAL) against
+    the reference's op sequence `relu(z) + conv(relu(z))` (neurips1_MGKN.py:76) -- oracle and this library's own plain
+    application -- on a graph with a hub, isolated nodes and duplicate edges, and on a chain of three steps."""
+    gen = torch.Generator().manual_seed(9)
+    N, E, w, kw = 260, 3000, 64, 64
+    src = torch.randint(0, N - 15, (E,), generator=gen)
+    dst = torch.randint(5, N, (E,), generator=gen)
+    src[:300] = 3
+    src[400:406], dst[400:406] = src[400], dst[400]
+    ei, ea = torch.stack([src, dst]), torch.rand(E, 6, generator=gen)
+    z = torch.randn(N, w, generator=gen)
+    ws, bs, root, bias = O.reference_init(w, w, [6, kw, kw, w * w], True, True, seed=3)
+    root = root if 'root' in flags else None
+    bias = bias if 'bias' in flags else None
+    conv = make_conv(_conv_cls(), ws, bs, root, bias, 'mean', w, w, precision, dev)
+    zd, eid, ead = z.to(dev), ei.to(dev), ea.to(dev)
+    x = torch.relu(z)
+    ref = x + O.nnconv_forward(x, ei, ea, ws, bs, root, bias, 'mean')
+    with torch.no_grad():
+        out = conv.residual_step(zd, eid, ead, relu_in=True)
+        plain = torch.relu(zd) + conv(torch.relu(zd), eid, ead)
+        out_lin = conv.residual_step(zd, eid, ead, relu_in=False)
+        plain_lin = zd + conv(zd, eid, ead)
+    assert rel_err(out, ref) < TOL[precision]
+    assert rel_err(out, plain) < 2e-6             # same kernels, only the fp32 summation order differs
+    assert rel_err(out_lin, plain_lin) < 2e-6
+    with torch.no_grad():                         # chain: z3 = step(step(step(z))) vs the op-by-op sequence
+        zc, pc = zd, zd
+        for k in range(3):
+            zc = conv.residual_step(zc, eid, ead, relu_in=k > 0)
+            a = torch.relu(pc) if k > 0 else pc
+            pc = a + conv(a, eid, ead)
+        assert rel_err(zc, pc) < 1e-4          # a 1e-7 difference can flip a 16-bit operand rounding of the next step
+    with pytest.raises(RuntimeError):
+        conv.residual_step(zd.clone().requires_grad_(True), eid, ead)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('ring_deep', [1, 0])
+def test_deep_y_ring_for_narrow_edge_networks(dev, ring_deep, lib_options, edge_kernel_mode):
+    """ker_width 128 -> 16 KB of Y per source, so the 48 MiB Y budget holds every one of the 1900 sources: the fused
+    kernel runs 15 batches of 128 sources through a 14-deep ring (`ring_deep`, default) instead of 3 batches of 640
+    through a 3-deep one; both schedules against the oracle, T = 3 applications."""
+    if edge_kernel_mode != 'off':
+        pytest.skip('the persistent fused kernel is the subject')
+    lib_options('ring_deep', ring_deep)
+    gen = torch.Generator().manual_seed(21)
+    N, S, w, kw = 2000, 1900, 64, 128
+    deg = torch.randint(8, 40, (S,), generator=gen)
+    src = torch.repeat_interleave(torch.arange(S), deg)
+    E = int(src.numel())
+    dst = torch.randint(0, N, (E,), generator=gen)
+    ei, ea = torch.stack([src, dst]), torch.rand(E, 6, generator=gen)
+    ws, bs, root, bias = O.reference_init(w, w, [6, kw, kw, w * w], True, True, seed=8)
+    conv = make_conv(_conv_cls(), ws, bs, root, bias, 'mean', w, w, 'f16', dev)
+    x = torch.randn(N, w, generator=gen)
+    xd, eid, ead = x.to(dev), ei.to(dev), ea.to(dev)
+    for _ in range(3):
+        ref = O.nnconv_forward(x, ei, ea, ws, bs, root, bias, 'mean')
+        with torch.no_grad():
+            out = conv(xd, eid, ead)
+        assert rel_err(out, ref) < TOL['f16']
+        x = torch.relu(ref)
+        xd = x.to(dev)
