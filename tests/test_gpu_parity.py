@@ -373,3 +373,31 @@ def test_deep_y_ring_for_narrow_edge_networks(dev, ring_deep, lib_options, edge_
         assert rel_err(out, ref) < TOL['f16']
         x = torch.relu(ref)
         xd = x.to(dev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('w', [32, 64])
+@pytest.mark.parametrize('precision', ['f16', 'bf16'])
+def test_per_edge_kernels_warp_per_source_and_warp_per_edge(dev, precision, w):
+    """Formulation B's two application kernels in their 16-byte-load form (in = out = 32 / 64): >= 2048 sources with 2-4
+    out-edges each run one warp per source (`k_apply_edge_src_v`), fewer sources one warp per edge (`k_apply_edge_v`)."""
+    from graph_pde_b200 import graphs, nn_conv
+    old = nn_conv._EDGE_KERNELS
+    nn_conv._EDGE_KERNELS = 'on'
+    try:
+        for s in (4096, 256):
+            X, eis, eas = graphs.multi_pole_grid1d(torch.randn(s, generator=torch.Generator().manual_seed(2)), s,
+                                                   is_periodic=True, levels=2)
+            ei, ea = eis[1], eas[1]
+            ws, bs, root, bias = O.reference_init(w, w, [4, 32, 32, w * w], True, True, seed=6)
+            x = torch.randn(s, w, generator=torch.Generator().manual_seed(3))
+            ref = O.nnconv_forward(x, ei, ea, ws, bs, root, bias, 'mean')
+            conv = make_conv(_conv_cls(), ws, bs, root, bias, 'mean', w, w, precision, dev)
+            with torch.no_grad():
+                out = conv(x.to(dev), ei.to(dev), ea.to(dev))
+                z = conv.residual_step(x.to(dev), ei.to(dev), ea.to(dev), relu_in=True)
+            assert rel_err(out, ref) < TOL[precision], (s, w)
+            xr = torch.relu(x)
+            assert rel_err(z, xr + O.nnconv_forward(xr, ei, ea, ws, bs, root, bias, 'mean')) < TOL[precision], (s, w)
+    finally:
+        nn_conv._EDGE_KERNELS = old
