@@ -18,7 +18,7 @@ const Entry kEntries[] = {
     {"no_fuse", "NNCONV_NO_FUSE", &Options::no_fuse, 0},
     {"no_pipe", "NNCONV_NO_PIPE", &Options::no_pipe, 0},
     {"ring", "NNCONV_RING", &Options::ring, 3},
-    {"ring_deep", "NNCONV_RING_DEEP", &Options::ring_deep, 1},
+    {"ring_deep", "NNCONV_RING_DEEP", &Options::ring_deep, 0},
     {"y_block_n", "NNCONV_Y_BLOCKN", &Options::y_block_n, 64},
     {"apply_stages", "NNCONV_APPLY_STAGES", &Options::apply_stages, 0},
     {"apply_passes", "NNCONV_APPLY_PASSES", &Options::apply_passes, 0},

@@ -8,10 +8,10 @@ struct Options {
   int no_fuse;            // NNCONV_NO_FUSE: per-batch Y GEMM + contraction kernels instead of the persistent fused kernel
   int no_pipe;            // NNCONV_NO_PIPE: plain stream order for the per-batch kernels (no PDL / flags)
   int ring;               // NNCONV_RING: Y ring depth of the fused kernel (2..8, default 3)
-  int ring_deep;          // NNCONV_RING_DEEP (default 1): when the Y budget holds more than ring x 128 sources (narrow edge
+  int ring_deep;          // NNCONV_RING_DEEP (default 0): when the Y budget holds more than ring x 128 sources (narrow edge
                           // networks: 32 KB of Y per source at ker_width 256), keep batches of 128 sources and deepen the
-                          // ring (<= 16) instead of growing the batches -- the contraction starts after the first 128
-                          // sources and the first `ring` batches never wait for a slot (small-graph latency)
+                          // ring (<= 16) instead of growing the batches.  Measured SLOWER on the MGKN V-cycle (1.86 vs
+                          // 1.61 ms per replayed forward, run r2v): more batches = more flag round trips per launch
   int y_block_n;          // NNCONV_Y_BLOCKN: N tile of the Y pipeline (64 default | 128)
   int apply_stages;       // NNCONV_APPLY_STAGES: cap on the A stages of the fused kernel (0 = no cap)
   int apply_passes;       // NNCONV_APPLY_PASSES: force the number of passes over the B-slot ring (0 = automatic): more

@@ -53,7 +53,8 @@ _KEEP_ACTS_MAX_BYTES = int(os.environ.get('NNCONV_B200_KEEP_ACTS_BYTES', str(64 
 # per-edge kernel matrices (formulation B) for graphs with few out-edges per source: auto | on | off
 _EDGE_KERNELS = os.environ.get('NNCONV_B200_EDGE_KERNELS', 'auto')
 _EDGE_KERNELS_MAX_DEG = 8                       # auto: average out-degree of the sources with out-edges ...
-_EDGE_KERNELS_MAX_EDGES = 8192                  # ... or a graph so small that streaming 8 KB per edge (<= 64 MB) costs less
+# ... or a graph so small that streaming 8 KB per edge (<= 64 MB) costs less
+_EDGE_KERNELS_MAX_EDGES = int(os.environ.get('NNCONV_B200_EDGE_KERNELS_MAX_EDGES', '8192'))
                                                 # than the fixed cost of the persistent kernel (MGKN's coarse levels)
 _EDGE_KERNELS_MAX_BYTES = 2 << 30
 

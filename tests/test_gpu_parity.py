@@ -350,8 +350,8 @@ def test_residual_step_equals_conv_add_on_preactivations(dev, precision, flags, 
 @pytest.mark.parametrize('ring_deep', [1, 0])
 def test_deep_y_ring_for_narrow_edge_networks(dev, ring_deep, lib_options, edge_kernel_mode):
     """ker_width 128 -> 16 KB of Y per source, so the 48 MiB Y budget holds every one of the 1900 sources: the fused
-    kernel runs 15 batches of 128 sources through a 14-deep ring (`ring_deep`, default) instead of 3 batches of 640
-    through a 3-deep one; both schedules against the oracle, T = 3 applications."""
+    kernel runs 15 batches of 128 sources through a 14-deep ring (option `ring_deep`) instead of 3 batches of 640
+    through a 3-deep one (default); both schedules against the oracle, T = 3 applications."""
     if edge_kernel_mode != 'off':
         pytest.skip('the persistent fused kernel is the subject')
     lib_options('ring_deep', ring_deep)
