@@ -189,3 +189,61 @@ def test_device_resident_loader_shares_the_mesh_and_caches_block_diagonal_index(
     assert batches[0].x.shape == (6, 2) and batches[0].batch.tolist() == [0, 0, 0, 1, 1, 1]
     single = next(iter(D.DataLoader(data, batch_size=1)))
     assert single is not data[0] and single.x is data[0].x                                   # shallow copy of the item
+
+
+def test_vcycle_step_chain_on_preactivations_equals_the_reference_op_sequence(monkeypatch):
+    """`KernelInduced` inference chains `residual_step` (z' = relu(z) + conv(relu(z)), last ReLU applied once);
+    with the CPU oracle standing in for the two conv entry points the chained forward must equal the reference's
+    conv / add / ReLU sequence and the golden output of the reference's own class (G4)."""
+    import numpy as np
+    from graph_pde_b200 import models, nn_conv
+    from tests.helpers import GOLDEN, ei64, t
+
+    def lin(conv):
+        ls = [m for m in conv.nn.layers if isinstance(m, torch.nn.Linear)]
+        return [l.weight.detach() for l in ls], [l.bias.detach() for l in ls]
+
+    def conv_forward(self, x, edge_index, edge_attr):
+        ws, bs = lin(self)
+        return O.nnconv_forward(x, edge_index, edge_attr, ws, bs, None if self.root is None else self.root.detach(),
+                                None if self.bias is None else self.bias.detach(), self.aggr)
+
+    calls = {'res': 0}
+
+    def residual_step(self, z, edge_index, edge_attr, relu_in=True):
+        calls['res'] += 1
+        x = torch.relu(z) if relu_in else z
+        return x + conv_forward(self, x, edge_index, edge_attr)
+
+    monkeypatch.setattr(nn_conv.NNConv_old, 'forward', conv_forward)
+    monkeypatch.setattr(nn_conv.NNConv_old, 'residual_step', residual_step)
+    g = np.load(os.path.join(GOLDEN, 'g4_mgkn_vcycle.npz'))
+    pts = [int(p) for p in g['points']]
+    model = models.KernelInduced(width=32, ker_width=64, depth=2, ker_in=6, points=pts, level=len(pts), in_width=6)
+    pre = 'neurips1/w/'
+    model.load_state_dict({k[len(pre):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(pre)})
+
+    class D(object):
+        pass
+    d = D()
+    d.x = t(g['node_x'])
+    for nm in ('mid', 'down', 'up'):
+        setattr(d, 'edge_index_' + nm, ei64(g['edge_index_' + nm]))
+        setattr(d, 'edge_attr_' + nm, t(g['edge_attr_' + nm]))
+    d.edge_index_range = torch.from_numpy(g['range_mid'])
+    d.edge_index_down_range = torch.from_numpy(g['range_down'])
+    d.edge_index_up_range = torch.from_numpy(g['range_up'])
+    with torch.no_grad():
+        monkeypatch.setattr(models, '_FUSED_STEPS', True)
+        fused = model(d)
+        n_res = calls['res']
+        monkeypatch.setattr(models, '_FUSED_STEPS', False)
+        plain = model(d)
+    assert n_res == 2 * (3 * len(pts) - 2) and calls['res'] == n_res       # 13 steps per depth iteration at 5 levels
+    ref = t(g['neurips1/out'])
+    assert float((fused - ref).abs().max() / ref.abs().max()) < 1e-5
+    assert float((fused - plain).abs().max() / ref.abs().max()) < 1e-5
+    # with gradients required the model must stay on the autograd-capable op sequence
+    monkeypatch.setattr(models, '_FUSED_STEPS', True)
+    out = model(d)
+    assert calls['res'] == n_res and out.requires_grad
