@@ -341,7 +341,8 @@ def test_residual_step_equals_conv_add_on_preactivations(dev, precision, flags, 
             zc = conv.residual_step(zc, eid, ead, relu_in=k > 0)
             a = torch.relu(pc) if k > 0 else pc
             pc = a + conv(a, eid, ead)
-        assert rel_err(zc, pc) < 1e-4          # a 1e-7 difference can flip a 16-bit operand rounding of the next step
+        # a 1e-7 summation-order difference can flip a 16-bit operand rounding of the next step (bf16: 8x coarser)
+        assert rel_err(zc, pc) < (1e-3 if precision == 'bf16' else 1e-4)
     with pytest.raises(RuntimeError):
         conv.residual_step(zd.clone().requires_grad_(True), eid, ead)
 
